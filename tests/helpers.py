@@ -1,0 +1,61 @@
+"""Shared test helpers (test infrastructure)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+REF = "/root/reference"
+STAGE = os.path.join(ROOT, "oracle", "_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def model_paths(which: str = "vntsr"):
+    """(param, bin) of the reference's exported detector.  Looks in /root/reference (authoring
+    container) then oracle/_ref (staged by build() for the GPU box).  bin is None when the
+    trained weights are unavailable (tt100k always; vntsr if nothing was staged): callers then
+    use seeded random weights of the same architecture."""
+    ref_dir = os.path.join(REF, f"src/{which}/convert/model/yolo_plus/yolo_plus_ncnn_model")
+    cands = [(os.path.join(ref_dir, "model.ncnn.param"), os.path.join(ref_dir, "model.ncnn.bin")),
+             (os.path.join(STAGE, f"{which}.model.ncnn.param"), os.path.join(STAGE, f"{which}.model.ncnn.bin")),
+             (os.path.join(GOLDEN, f"{which}.model.ncnn.param"), None)]
+    for p, b in cands:
+        if os.path.exists(p):
+            return p, (b if b and os.path.exists(b) else None)
+    raise FileNotFoundError(f"no model.ncnn.param for {which}")
+
+
+def onnx_path():
+    for p in (os.path.join(REF, "src/vntsr/convert/model/yolo_plus/yolo_plus.onnx"),
+              os.path.join(STAGE, "vntsr.yolo_plus.onnx")):
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def debug_roi_paths():
+    for d in (os.path.join(REF, "src/vntsr/pipeline/debug_rois"), os.path.join(STAGE, "debug_rois")):
+        if os.path.isdir(d):
+            return [os.path.join(d, f) for f in sorted(os.listdir(d))]
+    return []
+
+
+def oracle_pipeline_run(det_oracle, clf_model, frame, conf, iou, min_area):
+    """HybridPipeline.run (e2e.py:443-531) restated with the oracle pieces; returns result dicts
+    with the extra float32 box under 'box_f32'."""
+    from oracle import pipeline_ref as PR
+    x, r, pad, _ = PR.preprocess_ref(frame)
+    out0 = det_oracle.forward(x)[0].numpy()
+    boxes, scores, classes = PR.postprocess_ref(out0, frame.shape[:2], r, pad, conf, iou)
+    rois, valid = PR.roi_select_ref(boxes, frame.shape[:2], min_area)
+    crops = [frame[y1:y2, x1:x2] for (x1, y1, x2, y2) in rois]
+    cls, probs, _ = PR.classify_ref(clf_model, crops)
+    res = []
+    for j, k in enumerate(valid):
+        res.append({"bbox": tuple(boxes[k].astype(int)), "box_f32": boxes[k].astype(np.float32),
+                    "det_class": int(classes[k]), "det_conf": float(scores[k]),
+                    "cls_class": int(cls[j]), "cls_conf": float(np.max(probs[j]))})
+    return res

@@ -1,0 +1,78 @@
+// Shared declarations for the litepi_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/litepi_b200.h"
+
+#define LP_MAX_TABLE 64   // per-image metadata entries carried as kernel arguments per launch
+
+void lp_set_error(const char* fmt, ...);
+
+#define LP_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            lp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return -2;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define LP_CHECK(cond, ...)                  \
+    do {                                     \
+        if (!(cond)) {                       \
+            lp_set_error(__VA_ARGS__);       \
+            return -1;                       \
+        }                                    \
+    } while (0)
+
+#define LP_LAUNCH_OK(ctx)                                                                \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess) {                                                        \
+            lp_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return -2;                                                                   \
+        }                                                                                \
+    } while (0)
+
+struct lp_net_plan {
+    std::vector<lp_buf_desc> bufs;
+    std::vector<lp_op_desc> ops;
+    const float* weights = nullptr;
+    size_t n_floats = 0;
+    const uint8_t* weights_tc = nullptr;
+    size_t tc_bytes = 0;
+    int max_batch = 0;
+    size_t workspace_bytes = 0;     // max over bufs of offset + max_batch * image_bytes
+    bool loaded = false;
+};
+
+struct lp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int64_t launches = 0;
+    int use_tc = 1;
+    lp_net_plan nets[2];
+    void* tmaps_dev = nullptr;      // reserved
+};
+
+// ---- split-f16 helpers -------------------------------------------------------
+__device__ __forceinline__ float split_load(const __half* hi, const __half* lo, size_t i) {
+    return __half2float(hi[i]) + __half2float(lo[i]);
+}
+__device__ __forceinline__ void split_make(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// kernels implemented per translation unit (host launchers)
+int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, void* workspace,
+                size_t workspace_bytes, float* logits_or_head, cudaStream_t st);
+int lp_launch_detect_tail(lp_ctx* ctx, const float* head_raw, int batch, int head_c, float* out0, cudaStream_t st);
+
+// tensor-core path (conv_tc.cu); returns 1 if it handled the op, 0 if not applicable, <0 on error
+int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st);

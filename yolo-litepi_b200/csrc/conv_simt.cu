@@ -1,0 +1,508 @@
+// CUDA-core (SIMT) layer kernels: the generic fp32-FMA convolution family plus the memory-bound
+// glue ops.  They implement every layer of the detector (model.ncnn.param:4-183) and of
+// ShuffleNetV2 (torchvision shufflenetv2.py) and are the reference implementation the tcgen05
+// kernels in conv_tc.cu are checked against on the GPU.  Layers whose GEMM shape cannot feed the
+// tensor core (Cin = 3 or 8, N = 1, depthwise) stay here permanently: they are HBM-bound.
+//
+// Tensors are NHWC.  SPLIT16 buffers hold two fp16 planes (hi | lo), value = hi + lo.
+#include "common.cuh"
+
+struct TensorRef {
+    const void* base;        // SPLIT16: hi plane; F32/U8: the data
+    long long plane;         // SPLIT16: element offset from hi to lo plane
+    long long img;           // elements per image (per plane)
+    int C;                   // total channels of the buffer
+    int coff;                // first channel of the view
+    int fmt;
+};
+
+struct ConvParams {
+    TensorRef in, out, res;  // res.base == nullptr -> no residual
+    int cin, cout, out_cstride;
+    int H, W, Ho, Wo;        // input / output spatial size
+    int ksize, stride, act;
+    int n_img;
+    const float* w;          // [tap][cin][cout]
+    const float* bias;       // [cout]
+    float in_scale_mean, in_scale_std;   // STEM_U8: x = (u8/255 - mean)/std ; detector: mean 0, std 1
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == LP_ACT_SILU) return v / (1.f + __expf(-v));
+    if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+__device__ __forceinline__ float ld_elem(const TensorRef& t, long long idx) {
+    if (t.fmt == LP_FMT_SPLIT16) {
+        const __half* hi = (const __half*)t.base;
+        return __half2float(hi[idx]) + __half2float(hi[idx + t.plane]);
+    }
+    return ((const float*)t.base)[idx];
+}
+
+__device__ __forceinline__ void st_elem(const TensorRef& t, long long idx, float v) {
+    if (t.fmt == LP_FMT_SPLIT16) {
+        __half* hi = (__half*)t.base;
+        __half h, l;
+        split_make(v, h, l);
+        hi[idx] = h;
+        hi[idx + t.plane] = l;
+    } else {
+        ((float*)t.base)[idx] = v;
+    }
+}
+
+// Load 8 consecutive channels (16-B aligned for SPLIT16) as floats.
+__device__ __forceinline__ void ld8(const TensorRef& t, long long idx, float* v) {
+    if (t.fmt == LP_FMT_SPLIT16) {
+        const __half* hi = (const __half*)t.base;
+        uint4 a = *reinterpret_cast<const uint4*>(hi + idx);
+        uint4 b = *reinterpret_cast<const uint4*>(hi + idx + t.plane);
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 x = __half22float2(ah[i]), y = __half22float2(bh[i]);
+            v[2 * i] = x.x + y.x;
+            v[2 * i + 1] = x.y + y.y;
+        }
+    } else {
+        const float* p = (const float*)t.base + idx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = p[i];
+    }
+}
+
+__device__ __forceinline__ void st8(const TensorRef& t, long long idx, const float* v) {
+    if (t.fmt == LP_FMT_SPLIT16) {
+        __half* hi = (__half*)t.base;
+        uint4 a, b;
+        __half2* ah = reinterpret_cast<__half2*>(&a);
+        __half2* bh = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __half h0, l0, h1, l1;
+            split_make(v[2 * i], h0, l0);
+            split_make(v[2 * i + 1], h1, l1);
+            ah[i] = __halves2half2(h0, h1);
+            bh[i] = __halves2half2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(hi + idx) = a;
+        *reinterpret_cast<uint4*>(hi + idx + t.plane) = b;
+    } else {
+        float* p = (float*)t.base + idx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic conv: one thread = one output pixel x COB output channels; the block stages an input
+// patch [CK][PH][PW] (fp32) and a weight slab [taps][CK][COB] in shared memory per 8-channel chunk.
+// KS==1: the block covers 128 consecutive pixels of the flattened (image, y, x) index space.
+// KS==3: the block covers a 8x16 output tile of one image.
+// ---------------------------------------------------------------------------------------------
+constexpr int CONV_THREADS = 128;
+constexpr int TILE_W = 16, TILE_H = 8, CK = 8;
+
+template <int KS, int STRIDE, int COB>
+__global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(ConvParams p) {
+    constexpr int PH = (KS == 1) ? 1 : (TILE_H - 1) * STRIDE + KS;
+    constexpr int PW = (KS == 1) ? CONV_THREADS : (TILE_W - 1) * STRIDE + KS;
+    constexpr int TAPS = KS * KS;
+    __shared__ float s_patch[CK][PH][PW + 1];
+    __shared__ __align__(16) float s_w[TAPS][CK][COB];
+
+    const int tid = threadIdx.x;
+    const int co0 = blockIdx.y * COB;
+    int img, oy, ox;            // this thread's output pixel
+    int ty = 0, tx = tid;       // position inside the tile
+    long long pix0 = 0;         // KS==1: first flattened pixel of the block
+    int tile_y0 = 0, tile_x0 = 0;
+    bool valid;
+    if (KS == 1) {
+        pix0 = (long long)blockIdx.x * CONV_THREADS;
+        long long m = pix0 + tid;
+        long long total = (long long)p.n_img * p.Ho * p.Wo;
+        valid = m < total;
+        long long mm = valid ? m : 0;
+        img = (int)(mm / ((long long)p.Ho * p.Wo));
+        int r = (int)(mm - (long long)img * p.Ho * p.Wo);
+        oy = r / p.Wo;
+        ox = r - oy * p.Wo;
+    } else {
+        const int tiles_x = (p.Wo + TILE_W - 1) / TILE_W;
+        img = blockIdx.z;
+        tile_y0 = (blockIdx.x / tiles_x) * TILE_H;
+        tile_x0 = (blockIdx.x % tiles_x) * TILE_W;
+        ty = tid / TILE_W;
+        tx = tid % TILE_W;
+        oy = tile_y0 + ty;
+        ox = tile_x0 + tx;
+        valid = (oy < p.Ho && ox < p.Wo);
+    }
+
+    float acc[COB];
+#pragma unroll
+    for (int i = 0; i < COB; ++i) acc[i] = 0.f;
+
+    const int pad = KS / 2;
+    for (int c0 = 0; c0 < p.cin; c0 += CK) {
+        const int ck = min(CK, p.cin - c0);
+        // ---- stage input patch
+        if (KS == 1) {
+            // flattened pixels: (STRIDE==1 only) input pixel == output pixel
+            float v[CK];
+#pragma unroll
+            for (int i = 0; i < CK; ++i) v[i] = 0.f;
+            if (valid) {
+                long long idx = (long long)img * p.in.img + ((long long)oy * p.W + ox) * p.in.C + p.in.coff + c0;
+                if (ck == CK && p.in.fmt == LP_FMT_SPLIT16) ld8(p.in, idx, v);
+                else for (int i = 0; i < ck; ++i) v[i] = ld_elem(p.in, idx + i);
+            }
+#pragma unroll
+            for (int i = 0; i < CK; ++i) s_patch[i][0][tid] = v[i];
+        } else {
+            const int iy0 = tile_y0 * STRIDE - pad, ix0 = tile_x0 * STRIDE - pad;
+            for (int e = tid; e < PH * PW; e += CONV_THREADS) {
+                const int py = e / PW, px = e - py * PW;
+                const int iy = iy0 + py, ix = ix0 + px;
+                float v[CK];
+#pragma unroll
+                for (int i = 0; i < CK; ++i) v[i] = 0.f;
+                if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                    long long idx = (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff + c0;
+                    if (ck == CK && p.in.fmt == LP_FMT_SPLIT16) ld8(p.in, idx, v);
+                    else for (int i = 0; i < ck; ++i) v[i] = ld_elem(p.in, idx + i);
+                }
+#pragma unroll
+                for (int i = 0; i < CK; ++i) s_patch[i][py][px] = v[i];
+            }
+        }
+        // ---- stage weights [tap][ci][co]
+        for (int e = tid; e < TAPS * CK * COB; e += CONV_THREADS) {
+            const int co = e % COB, ci = (e / COB) % CK, t = e / (COB * CK);
+            float wv = 0.f;
+            if (ci < ck && co0 + co < p.cout) wv = __ldg(p.w + ((long long)t * p.cin + c0 + ci) * p.cout + co0 + co);
+            s_w[t][ci][co] = wv;
+        }
+        __syncthreads();
+        // ---- FMA
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+            const int ky = t / KS, kx = t % KS;
+#pragma unroll
+            for (int ci = 0; ci < CK; ++ci) {
+                const float a = (KS == 1) ? s_patch[ci][0][tid] : s_patch[ci][ty * STRIDE + ky][tx * STRIDE + kx];
+                const float4* wr = reinterpret_cast<const float4*>(&s_w[t][ci][0]);
+#pragma unroll
+                for (int q = 0; q < COB / 4; ++q) {
+                    const float4 w4 = wr[q];
+                    acc[4 * q + 0] = fmaf(a, w4.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(a, w4.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(a, w4.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(a, w4.w, acc[4 * q + 3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!valid) return;
+    // ---- epilogue: bias, activation, residual, store
+    const long long opix = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff;
+    const long long rpix = p.res.base ? (long long)img * p.res.img + ((long long)oy * p.Wo + ox) * p.res.C + p.res.coff : 0;
+#pragma unroll
+    for (int g = 0; g < COB / 8; ++g) {
+        const int cbase = co0 + g * 8;
+        if (cbase >= p.cout) break;
+        float v[8];
+        const int n = min(8, p.cout - cbase);
+        float r[8];
+        if (p.res.base) {
+            if (n == 8 && p.res.fmt == LP_FMT_SPLIT16) ld8(p.res, rpix + cbase, r);
+            else for (int i = 0; i < n; ++i) r[i] = ld_elem(p.res, rpix + cbase + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float x = acc[g * 8 + i] + (i < n ? __ldg(p.bias + cbase + i) : 0.f);
+            x = act_apply(x, p.act);
+            if (p.res.base && i < n) x += r[i];
+            v[i] = x;
+        }
+        if (n == 8 && p.out_cstride == 1 && (p.out.fmt == LP_FMT_SPLIT16)) st8(p.out, opix + cbase, v);
+        else for (int i = 0; i < n; ++i) st_elem(p.out, opix + (long long)(cbase + i) * p.out_cstride, v[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem: 3x3 stride-2 conv straight from the u8 RGB image (letterbox / ROI-resize output).
+// x = (u8/255 - mean)/std with IEEE divisions exactly as ToTensor/Normalize (e2e.py:368-369)
+// and the ORT twin's x/255 (evaluation_tsd_single_img.ipynb:98-110) compute it.
+// ---------------------------------------------------------------------------------------------
+template <int COB>
+__global__ void __launch_bounds__(CONV_THREADS) stem_u8_kernel(ConvParams p) {
+    constexpr int PH = (TILE_H - 1) * 2 + 3, PW = (TILE_W - 1) * 2 + 3;
+    __shared__ float s_patch[3][PH][PW + 1];
+    __shared__ __align__(16) float s_w[9][3][COB];
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.Wo + TILE_W - 1) / TILE_W;
+    const int img = blockIdx.z;
+    const int tile_y0 = (blockIdx.x / tiles_x) * TILE_H, tile_x0 = (blockIdx.x % tiles_x) * TILE_W;
+    const int ty = tid / TILE_W, tx = tid % TILE_W;
+    const int oy = tile_y0 + ty, ox = tile_x0 + tx;
+    const int co0 = blockIdx.y * COB;
+    const uint8_t* src = (const uint8_t*)p.in.base + (long long)img * p.in.img;
+    const int iy0 = tile_y0 * 2 - 1, ix0 = tile_x0 * 2 - 1;
+    for (int e = tid; e < PH * PW; e += CONV_THREADS) {
+        const int py = e / PW, px = e - py * PW;
+        const int iy = iy0 + py, ix = ix0 + px;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+            const uint8_t* q = src + ((long long)iy * p.W + ix) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float x = __fdiv_rn((float)q[c], 255.f);
+                if (p.in_scale_std != 1.f || p.in_scale_mean != 0.f)
+                    x = __fdiv_rn(__fsub_rn(x, p.in_scale_mean), p.in_scale_std);
+                v[c] = x;
+            }
+        }
+        s_patch[0][py][px] = v[0]; s_patch[1][py][px] = v[1]; s_patch[2][py][px] = v[2];
+    }
+    for (int e = tid; e < 9 * 3 * COB; e += CONV_THREADS) {
+        const int co = e % COB, ci = (e / COB) % 3, t = e / (COB * 3);
+        s_w[t][ci][co] = (co0 + co < p.cout) ? __ldg(p.w + ((long long)t * 3 + ci) * p.cout + co0 + co) : 0.f;
+    }
+    __syncthreads();
+    if (oy >= p.Ho || ox >= p.Wo) return;
+    float acc[COB];
+#pragma unroll
+    for (int i = 0; i < COB; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+            const float a = s_patch[ci][ty * 2 + t / 3][tx * 2 + t % 3];
+#pragma unroll
+            for (int co = 0; co < COB; ++co) acc[co] = fmaf(a, s_w[t][ci][co], acc[co]);
+        }
+    }
+    const long long opix = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff;
+#pragma unroll
+    for (int g = 0; g < COB / 8; ++g) {
+        const int cbase = co0 + g * 8;
+        if (cbase >= p.cout) break;
+        const int n = min(8, p.cout - cbase);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = act_apply(acc[g * 8 + i] + (i < n ? __ldg(p.bias + cbase + i) : 0.f), p.act);
+        if (n == 8 && p.out.fmt == LP_FMT_SPLIT16) st8(p.out, opix + cbase, v);
+        else for (int i = 0; i < n; ++i) st_elem(p.out, opix + cbase + i, v[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Memory-bound glue: depthwise 3x3, max pool, nearest x2 upsample, channel-slice copy, mean+FC.
+// One thread per (pixel, channel); channels fastest so warps read/write contiguous NHWC runs.
+// ---------------------------------------------------------------------------------------------
+__global__ void dwconv3_kernel(ConvParams p) {
+    const long long total = (long long)p.n_img * p.Ho * p.Wo * p.cout;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % p.cout);
+    long long r = i / p.cout;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int img = (int)(r / p.Ho);
+    float acc = __ldg(p.bias + c);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * p.stride - 1 + ky;
+        if (iy < 0 || iy >= p.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * p.stride - 1 + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            const float a = ld_elem(p.in, (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff + c);
+            acc = fmaf(a, __ldg(p.w + (ky * 3 + kx) * p.cout + c), acc);
+        }
+    }
+    acc = act_apply(acc, p.act);
+    st_elem(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + (long long)c * p.out_cstride, acc);
+}
+
+__global__ void maxpool_kernel(ConvParams p) {
+    const long long total = (long long)p.n_img * p.Ho * p.Wo * p.cout;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % p.cout);
+    long long r = i / p.cout;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int img = (int)(r / p.Ho);
+    const int pad = p.ksize / 2;
+    float m = -INFINITY;
+    for (int ky = 0; ky < p.ksize; ++ky) {
+        const int iy = oy * p.stride - pad + ky;
+        if (iy < 0 || iy >= p.H) continue;
+        for (int kx = 0; kx < p.ksize; ++kx) {
+            const int ix = ox * p.stride - pad + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            m = fmaxf(m, ld_elem(p.in, (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff + c));
+        }
+    }
+    st_elem(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + c, m);
+}
+
+// upsample x2 (stride field = 2) or plain copy (stride = 1); out pixel (oy,ox) <- in (oy/s, ox/s)
+__global__ void resample_copy_kernel(ConvParams p) {
+    const long long total = (long long)p.n_img * p.Ho * p.Wo * p.cout;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % p.cout);
+    long long r = i / p.cout;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int img = (int)(r / p.Ho);
+    const int iy = oy / p.stride, ix = ox / p.stride;
+    const long long src = (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff + c;
+    const long long dst = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + (long long)c * p.out_cstride;
+    if (p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16) {   // bit-preserving
+        const __half* s = (const __half*)p.in.base;
+        __half* d = (__half*)p.out.base;
+        d[dst] = s[src];
+        d[dst + p.out.plane] = s[src + p.in.plane];
+    } else {
+        st_elem(p.out, dst, ld_elem(p.in, src));
+    }
+}
+
+// global mean over HxW then FC: logits[img][j] = bias[j] + sum_c mean_c * w[c][j]   (w stored [cin][cout])
+__global__ void mean_fc_kernel(ConvParams p, float* __restrict__ logits) {
+    extern __shared__ float s_mean[];
+    const int img = blockIdx.x;
+    const int hw = p.H * p.W;
+    for (int c = threadIdx.x; c < p.cin; c += blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < hw; ++q) s += ld_elem(p.in, (long long)img * p.in.img + (long long)q * p.in.C + p.in.coff + c);
+        s_mean[c] = s / (float)hw;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < p.cout; j += blockDim.x) {
+        float acc = __ldg(p.bias + j);
+        for (int c = 0; c < p.cin; ++c) acc = fmaf(s_mean[c], __ldg(p.w + (long long)c * p.cout + j), acc);
+        logits[(long long)img * p.cout + j] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plan executor
+// ---------------------------------------------------------------------------------------------
+static TensorRef make_ref(const lp_net_plan& net, int buf, int coff, uint8_t* ws, int row_off) {
+    TensorRef t{};
+    if (buf < 0) { t.base = nullptr; return t; }
+    const lp_buf_desc& b = net.bufs[buf];
+    const int esz = b.fmt == LP_FMT_SPLIT16 ? 2 : (b.fmt == LP_FMT_F32 ? 4 : 1);
+    t.base = ws + b.offset + (size_t)row_off * b.c * esz;
+    t.img = b.image_bytes / esz;
+    t.plane = (b.fmt == LP_FMT_SPLIT16) ? (long long)net.max_batch * t.img : 0;
+    t.C = b.c;
+    t.coff = coff;
+    t.fmt = b.fmt;
+    return t;
+}
+
+template <int KS, int STRIDE>
+static void launch_conv(const ConvParams& p, cudaStream_t st) {
+    const int cob = (p.cout % 32 == 0 || p.cout > 32) ? 32 : (p.cout > 8 ? 16 : 8);
+    dim3 grid;
+    if (KS == 1) grid = dim3((unsigned)(((long long)p.n_img * p.Ho * p.Wo + CONV_THREADS - 1) / CONV_THREADS), (p.cout + cob - 1) / cob, 1);
+    else grid = dim3(((p.Wo + TILE_W - 1) / TILE_W) * ((p.Ho + TILE_H - 1) / TILE_H), (p.cout + cob - 1) / cob, p.n_img);
+    if (cob == 32) conv_simt_kernel<KS, STRIDE, 32><<<grid, CONV_THREADS, 0, st>>>(p);
+    else if (cob == 16) conv_simt_kernel<KS, STRIDE, 16><<<grid, CONV_THREADS, 0, st>>>(p);
+    else conv_simt_kernel<KS, STRIDE, 8><<<grid, CONV_THREADS, 0, st>>>(p);
+}
+
+int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, void* workspace,
+                size_t workspace_bytes, float* logits, cudaStream_t st) {
+    LP_CHECK(net.loaded, "lp_run_plan: network not loaded");
+    LP_CHECK(batch >= 1 && batch <= net.max_batch, "lp_run_plan: batch %d outside [1, %d]", batch, net.max_batch);
+    LP_CHECK(workspace_bytes >= net.workspace_bytes, "lp_run_plan: workspace %zu B < required %zu B",
+             workspace_bytes, net.workspace_bytes);
+    uint8_t* ws = (uint8_t*)workspace;
+    for (size_t oi = 0; oi < net.ops.size(); ++oi) {
+        const lp_op_desc& op = net.ops[oi];
+        ConvParams p{};
+        const lp_buf_desc& ob = net.bufs[op.out_buf >= 0 ? op.out_buf : op.in_buf];
+        p.cin = op.cin; p.cout = op.cout; p.out_cstride = op.out_cstride > 0 ? op.out_cstride : 1;
+        p.ksize = op.ksize; p.stride = op.stride; p.act = op.act; p.n_img = batch;
+        p.w = net.weights + op.w_off; p.bias = net.weights + op.b_off;
+        p.in_scale_mean = 0.f; p.in_scale_std = 1.f;
+        if (op.kind == LP_OP_STEM_U8) {
+            // the network input is the caller's u8 image tensor, not a workspace buffer
+            const lp_buf_desc& ib = net.bufs[op.in_buf];
+            p.in.base = in; p.in.img = (long long)ib.h * ib.w * 3; p.in.C = 3; p.in.coff = 0; p.in.fmt = LP_FMT_U8;
+            p.H = ib.h; p.W = ib.w;
+            p.in_scale_mean = op.in_mean; p.in_scale_std = op.in_std;
+        } else {
+            const lp_buf_desc& ib = net.bufs[op.in_buf];
+            p.in = make_ref(net, op.in_buf, op.in_coff, ws, 0);
+            p.H = ib.h; p.W = ib.w;
+            if (op.kind == LP_OP_CONV) p.res = make_ref(net, op.res_buf, op.res_coff, ws, 0);
+        }
+        if (op.kind != LP_OP_MEAN_FC) {
+            p.out = make_ref(net, op.out_buf, op.out_coff, ws, op.row_off);
+            p.Ho = (op.kind == LP_OP_UPSAMPLE2) ? p.H * 2 : (op.kind == LP_OP_COPY ? p.H : (p.H + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
+            p.Wo = (op.kind == LP_OP_UPSAMPLE2) ? p.W * 2 : (op.kind == LP_OP_COPY ? p.W : (p.W + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
+            if (!(ob.w == 1 && ob.h > 1))     // Detect-head row buffers ([anchors][C]) are addressed through row_off
+                LP_CHECK(ob.h == p.Ho && ob.w == p.Wo, "op %zu: output buffer %dx%d != computed %dx%d", oi, ob.h, ob.w, p.Ho, p.Wo);
+        }
+        const long long total = (long long)batch * p.Ho * p.Wo * p.cout;
+        switch (op.kind) {
+        case LP_OP_STEM_U8: {
+            LP_CHECK(op.ksize == 3 && op.stride == 2 && op.cout <= 32, "stem: unsupported shape");
+            dim3 grid(((p.Wo + TILE_W - 1) / TILE_W) * ((p.Ho + TILE_H - 1) / TILE_H), 1, batch);
+            if (op.cout <= 8) stem_u8_kernel<8><<<grid, CONV_THREADS, 0, st>>>(p);
+            else if (op.cout <= 16) stem_u8_kernel<16><<<grid, CONV_THREADS, 0, st>>>(p);
+            else if (op.cout <= 24) stem_u8_kernel<24><<<grid, CONV_THREADS, 0, st>>>(p);
+            else stem_u8_kernel<32><<<grid, CONV_THREADS, 0, st>>>(p);
+            break;
+        }
+        case LP_OP_CONV: {
+            if (ctx->use_tc && op.wtc_off >= 0 && net.weights_tc) {
+                int r = lp_conv_tc_try(ctx, net, op, batch, ws, st);
+                if (r < 0) return r;
+                if (r == 1) { ctx->launches++; continue; }
+            }
+            if (op.ksize == 1) { LP_CHECK(op.stride == 1, "1x1 conv must have stride 1"); launch_conv<1, 1>(p, st); }
+            else if (op.ksize == 3 && op.stride == 1) launch_conv<3, 1>(p, st);
+            else if (op.ksize == 3 && op.stride == 2) launch_conv<3, 2>(p, st);
+            else LP_CHECK(false, "conv: unsupported ksize %d stride %d", op.ksize, op.stride);
+            break;
+        }
+        case LP_OP_DWCONV3:
+            dwconv3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+            break;
+        case LP_OP_MAXPOOL:
+            maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+            break;
+        case LP_OP_UPSAMPLE2:
+            p.stride = 2;
+            resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+            break;
+        case LP_OP_COPY:
+            p.stride = 1;
+            resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+            break;
+        case LP_OP_MEAN_FC:
+            LP_CHECK(logits != nullptr, "mean_fc: logits pointer is null");
+            mean_fc_kernel<<<batch, 256, op.cin * sizeof(float), st>>>(p, logits);
+            break;
+        default:
+            LP_CHECK(false, "unknown op kind %d", op.kind);
+        }
+        LP_LAUNCH_OK(ctx);
+    }
+    return 0;
+}

@@ -1,0 +1,198 @@
+"""B200Pipeline -- drop-in for the reference's ``HybridPipeline``
+(``src/vntsr/pipeline/e2e.py:399-531``) plus the batched / device-resident entry
+points the B200 needs (``run_batch``, ``run_device``).
+
+Stage order per batch, all on one CUDA stream:
+  H2D -> K1 letterbox -> K2/K3 detector -> K4 decode+threshold -> K5 NMS -> ROI select
+      -> (4-byte D2H of the ROI count) -> K6 crop+resize -> K7 ShuffleNetV2 -> pack -> D2H records
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .classifier import B200Classifier
+from .detector import B200Detector, FrameBatch, _ptr, _stream
+
+
+@dataclass
+class PipelineMetrics:
+    """Field-for-field the reference's dataclass (e2e.py:34-62)."""
+    t_detection: float = 0.0
+    t_roi_extract: float = 0.0
+    t_classification: float = 0.0
+    t_postprocess: float = 0.0
+    t_total: float = 0.0
+    fps: float = 0.0
+    num_detections: int = 0
+    det_confidence_avg: float = 0.0
+    cls_confidence_avg: float = 0.0
+    cpu_percent: float = 0.0
+    memory_mb: float = 0.0
+    temperature: float = 0.0
+    precision: float = 0.0
+    recall: float = 0.0
+    f1: float = 0.0
+    level: str = "B200"
+
+
+REC_WORDS = 9   # frame_id, x1,y1,x2,y2, det_conf, det_cls, cls_cls, cls_conf
+
+
+class B200Pipeline:
+    def __init__(self, detector_param: str, detector_bin: Optional[str], classifier_path: Optional[str],
+                 classifier_arch: str = "shufflenetv2", num_classes: int = 58, det_input_size: int = 640,
+                 cls_input_size: int = 64, use_gpu_detector: bool = False, detector_threads: int = 4,
+                 classifier_device: str = "cpu", batch_size: int = 8,
+                 device: int = 0, max_batch: int = 64, max_det: int = 1024, max_rois: Optional[int] = None,
+                 classifier_state_dict: Optional[dict] = None, seed: Optional[int] = None):
+        self.detector = B200Detector(detector_param, detector_bin, input_size=det_input_size,
+                                     use_gpu=use_gpu_detector, num_threads=detector_threads,
+                                     device=device, max_batch=max_batch, max_det=max_det, seed=seed or 0)
+        self.classifier = B200Classifier(classifier_path, classifier_arch, num_classes=num_classes,
+                                         input_size=cls_input_size, device=classifier_device,
+                                         state_dict=classifier_state_dict, cuda_device=device, seed=seed)
+        self.batch_size = batch_size          # reference's classifier mini-batch; ROIs are classified in one pass here
+        self.device = self.detector.device
+        self.ctx = self.detector.ctx
+        self.max_batch = int(max_batch)
+        self.max_rois = int(max_rois) if max_rois else self.max_batch * 64
+        with torch.cuda.device(self.device):
+            R = self.max_rois
+            self.roi_xyxy = torch.empty((R, 4), dtype=torch.int32, device=self.device)
+            self.roi_src = torch.empty((R, 2), dtype=torch.int32, device=self.device)
+            self.n_rois = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            self.records = torch.empty((R, REC_WORDS), dtype=torch.int32, device=self.device)
+            self.n_rois_h = torch.zeros((1,), dtype=torch.int32).pin_memory()
+            self.records_h = torch.empty((R, REC_WORDS), dtype=torch.int32).pin_memory()
+            self.counts_h = torch.zeros((self.max_batch,), dtype=torch.int32).pin_memory()
+
+    # ------------------------------------------------------------------ device path
+    def run_device(self, fb: FrameBatch, conf_threshold: float = 0.5, iou_threshold: float = 0.45,
+                   min_area: int = 100, frame_ids: Optional[torch.Tensor] = None) -> int:
+        """Whole hot path on device-resident frames.  Returns the ROI count; records for them are in
+        ``self.records[:n]`` (device).  One tiny D2H (the ROI count) sizes the classifier launches."""
+        det, clf, lib = self.detector, self.classifier, L.lib()
+        det.detect_device(fb, conf_threshold, iou_threshold)
+        L.check(lib.lp_roi_select(self.ctx.handle, _ptr(det.boxes), _ptr(det.counts), det.max_det, fb.h, fb.w, fb.n,
+                                  int(min_area), self.max_rois, _ptr(self.roi_xyxy), _ptr(self.roi_src),
+                                  _ptr(self.n_rois), _stream()), "lp_roi_select")
+        self.n_rois_h.copy_(self.n_rois, non_blocking=True)
+        self.counts_h[:fb.n].copy_(det.counts[:fb.n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = int(self.n_rois_h[0])
+        if n > self.max_rois:
+            raise RuntimeError(f"litepi_b200: {n} ROIs exceed max_rois={self.max_rois}")
+        if fb.n and int(self.counts_h[:fb.n].max()) > det.max_det:
+            raise RuntimeError(f"litepi_b200: a frame has more than max_det={det.max_det} detections")
+        if n:
+            cls_in = clf.resize_device(fb, self.roi_xyxy, self.roi_src, n)
+            clf.classify_device(cls_in)
+            L.check(lib.lp_pack_records(self.ctx.handle, _ptr(self.roi_src), _ptr(frame_ids), _ptr(det.boxes),
+                                        _ptr(det.scores), _ptr(det.classes), det.max_det, _ptr(clf.argmax),
+                                        _ptr(clf.probs), clf.num_classes, n, _ptr(self.records), _stream()),
+                    "lp_pack_records")
+        return n
+
+    def fetch_records(self, n: int) -> np.ndarray:
+        """D2H of ``n`` packed records -> structured numpy view [n] (blocking)."""
+        if n == 0:
+            return np.zeros((0, REC_WORDS), np.int32)
+        self.records_h[:n].copy_(self.records[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.records_h[:n].numpy().copy()
+
+    @staticmethod
+    def records_to_results(rec: np.ndarray, n_frames: int) -> List[List[Dict]]:
+        """Packed records -> per-frame result dict lists (keys of e2e.py:519-529)."""
+        out: List[List[Dict]] = [[] for _ in range(n_frames)]
+        if rec.shape[0] == 0:
+            return out
+        f = rec.view(np.float32)
+        for i in range(rec.shape[0]):
+            box = f[i, 1:5]
+            out[int(rec[i, 0])].append({
+                "bbox": tuple(box.astype(int)),
+                "box_f32": box.copy(),
+                "det_class": int(rec[i, 6]),
+                "det_conf": float(f[i, 5]),
+                "cls_class": int(rec[i, 7]),
+                "cls_conf": float(f[i, 8]),
+            })
+        return out
+
+    # ------------------------------------------------------------------ batched host API
+    def run_batch(self, images: Sequence[np.ndarray], conf_threshold: float = 0.5, iou_threshold: float = 0.45,
+                  min_area: int = 100) -> List[List[Dict]]:
+        """Batched form of ``run``: list of frames -> list (per frame) of result dicts."""
+        results: List[List[Dict]] = []
+        for i in range(0, len(images), self.max_batch):
+            chunk = images[i:i + self.max_batch]
+            fb = FrameBatch.from_host(chunk, self.device)
+            n = self.run_device(fb, conf_threshold, iou_threshold, min_area)
+            results.extend(self.records_to_results(self.fetch_records(n), len(chunk)))
+        return results
+
+    # ------------------------------------------------------------------ reference API
+    def run(self, image: np.ndarray, conf_threshold: float = 0.5, iou_threshold: float = 0.45,
+            min_area: int = 100) -> Tuple[List[Dict], PipelineMetrics]:
+        """e2e.py:443-531.  Stage times come from CUDA events on the launching stream."""
+        m = PipelineMetrics(level="B200")
+        t_start = time.perf_counter()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        det, clf, lib = self.detector, self.classifier, L.lib()
+        fb = FrameBatch.from_host([image], self.device)
+        ev[0].record()
+        det.detect_device(fb, conf_threshold, iou_threshold)
+        ev[1].record()
+        L.check(lib.lp_roi_select(self.ctx.handle, _ptr(det.boxes), _ptr(det.counts), det.max_det, fb.h, fb.w, 1,
+                                  int(min_area), self.max_rois, _ptr(self.roi_xyxy), _ptr(self.roi_src),
+                                  _ptr(self.n_rois), _stream()), "lp_roi_select")
+        ev[2].record()
+        dets = det._collect(1)[0]                      # syncs; reference counts pre-filter detections (e2e.py:454)
+        m.num_detections = len(dets[0])
+        if len(dets[1]) > 0:
+            m.det_confidence_avg = float(np.mean(dets[1]))
+        n = int(self.n_rois.cpu()[0])
+        if n > self.max_rois:
+            raise RuntimeError(f"litepi_b200: {n} ROIs exceed max_rois={self.max_rois}")
+        if n:
+            cls_in = clf.resize_device(fb, self.roi_xyxy, self.roi_src, n)
+            clf.classify_device(cls_in)
+        ev[3].record()
+        ev[3].synchronize()
+        m.t_detection = ev[0].elapsed_time(ev[1])
+        m.t_roi_extract = ev[1].elapsed_time(ev[2])
+        m.t_classification = ev[2].elapsed_time(ev[3])
+        results: List[Dict] = []
+        if n:
+            src = self.roi_src[:n].cpu().numpy()
+            probs = clf.probs[:n].cpu().numpy()
+            cls_ids = np.argmax(probs, axis=1)
+            m.cls_confidence_avg = float(np.mean(probs.max(axis=1)))
+            for r in range(n):
+                k = int(src[r, 1])
+                results.append({
+                    "bbox": tuple(dets[0][k].astype(int)),
+                    "det_class": int(dets[2][k]),
+                    "det_conf": float(dets[1][k]),
+                    "cls_class": int(cls_ids[r]),
+                    "cls_conf": float(np.max(probs[r])),
+                    "time_det": m.t_detection / n,
+                    "time_cls": m.t_classification / n,
+                })
+        m.t_total = (time.perf_counter() - t_start) * 1000
+        m.fps = 1000.0 / m.t_total if m.t_total > 0 else 0
+        try:
+            import psutil
+            m.cpu_percent = psutil.cpu_percent()
+            m.memory_mb = psutil.Process().memory_info().rss / 1024 / 1024
+        except Exception:
+            pass
+        return results, m

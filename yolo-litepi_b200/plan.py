@@ -1,0 +1,419 @@
+"""Lowers the two networks of the hot path to flat launch plans (``lp_op_desc`` lists).
+
+Detector: the reference's exported graph (``model.ncnn.param``; Ultralytics YAML at
+``train_model/train-yolo-custom-vntsr..ipynb:1918-1960``) is a YOLOv8-family template:
+Conv, Conv, C2f, Conv, C2f, Conv, C2f, Conv, C2f, SPPF, (Upsample, Concat, C2f) x2,
+(Conv, Concat, C2f) x2, Detect.  Widths and C2f depths are read from the file; the
+template consumes the Convolution records in file order and checks every shape.
+
+Everything that is a view in the graph stays a view here: C2f chunk/concat, SPPF
+concat, the neck concats and ShuffleNetV2's chunk + channel_shuffle become channel
+offsets / strides of the producing kernel's store (no concat or shuffle kernels).
+
+Classifier: torchvision ``shufflenet_v2_x1_0`` (``e2e.py:331-333``) from its
+``state_dict``, BatchNorm folded into the convs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .ncnn_model import ConvRec, NcnnModel
+
+
+def p8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+@dataclass
+class View:
+    """A run of logical channel segments inside one buffer; segment i holds ``lens[i]``
+    real channels starting at physical channel ``offs[i]`` (padded to 8 for split-f16)."""
+    buf: int
+    offs: Tuple[int, ...]
+    lens: Tuple[int, ...]
+    pad8: bool = True
+
+    @property
+    def start(self) -> int:
+        return self.offs[0]
+
+    @property
+    def phys(self) -> int:
+        last = self.lens[-1]
+        return self.offs[-1] + (p8(last) if self.pad8 else last) - self.offs[0]
+
+    @property
+    def logical(self) -> int:
+        return sum(self.lens)
+
+    def chan_map(self) -> np.ndarray:
+        """physical index (relative to start) of every logical channel"""
+        idx = []
+        for o, n in zip(self.offs, self.lens):
+            idx.extend(range(o - self.offs[0], o - self.offs[0] + n))
+        return np.asarray(idx, dtype=np.int64)
+
+    def seg(self, i: int, j: Optional[int] = None) -> "View":
+        j = i + 1 if j is None else j
+        return View(self.buf, self.offs[i:j], self.lens[i:j], self.pad8)
+
+
+@dataclass
+class Plan:
+    bufs: List[dict] = field(default_factory=list)
+    ops: List[dict] = field(default_factory=list)
+    blobs: List[np.ndarray] = field(default_factory=list)
+    n_floats: int = 0
+    names: List[str] = field(default_factory=list)
+    macs: List[int] = field(default_factory=list)          # per op, per image
+    meta: Dict[str, object] = field(default_factory=dict)
+
+    # ---- buffers
+    def buf(self, h: int, w: int, c: int, fmt: int) -> int:
+        self.bufs.append(dict(h=h, w=w, c=c, fmt=fmt))
+        return len(self.bufs) - 1
+
+    def new_view(self, h: int, w: int, lens: Sequence[int], fmt: int = L.FMT_SPLIT16) -> View:
+        pad8 = fmt == L.FMT_SPLIT16
+        offs, o = [], 0
+        for n in lens:
+            offs.append(o)
+            o += p8(n) if pad8 else n
+        return View(self.buf(h, w, o, fmt), tuple(offs), tuple(lens), pad8)
+
+    # ---- weights
+    def _push(self, a: np.ndarray) -> int:
+        a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+        off = self.n_floats
+        self.blobs.append(a)
+        self.n_floats += a.size
+        pad = (-self.n_floats) % 4                      # keep every tensor 16-B aligned
+        if pad:
+            self.blobs.append(np.zeros(pad, np.float32))
+            self.n_floats += pad
+        return off
+
+    def weights(self) -> np.ndarray:
+        return np.concatenate(self.blobs) if self.blobs else np.zeros(0, np.float32)
+
+    # ---- ops
+    def conv(self, name: str, w: np.ndarray, b: Optional[np.ndarray], src: View, dst: View, stride: int, act: int,
+             res: Optional[View] = None, row_off: int = 0, out_cstride: int = 1, kind: int = L.OP_CONV,
+             in_mean: float = 0.0, in_std: float = 1.0) -> None:
+        """w: [cout, cin, k, k] (logical channels) -> packed [tap][cin_phys][cout_phys], zero padded."""
+        cout, cin, k, _ = w.shape
+        assert cin == src.logical, f"{name}: cin {cin} != view {src.logical}"
+        assert cout == dst.logical, f"{name}: cout {cout} != view {dst.logical}"
+        hi, wi = self.bufs[src.buf]["h"], self.bufs[src.buf]["w"]
+        cinp = src.phys if kind != L.OP_STEM_U8 else 3
+        coutp = dst.phys if out_cstride == 1 else cout
+        wp = np.zeros((k * k, cinp, coutp), np.float32)
+        im = src.chan_map() if kind != L.OP_STEM_U8 else np.arange(3)
+        om = dst.chan_map() if out_cstride == 1 else np.arange(cout)
+        wp[:, im[:, None], om[None, :]] = w.transpose(2, 3, 1, 0).reshape(k * k, cin, cout)
+        bp = np.zeros(coutp, np.float32)
+        if b is not None:
+            bp[om] = b
+        if res is not None:
+            assert res.logical == cout and res.phys == coutp
+        ho = (hi + 2 * (k // 2) - k) // stride + 1
+        wo = (wi + 2 * (k // 2) - k) // stride + 1
+        self.ops.append(dict(kind=kind, in_buf=src.buf, in_coff=src.start if kind != L.OP_STEM_U8 else 0, cin=cinp,
+                             out_buf=dst.buf, out_coff=dst.start, cout=coutp, out_cstride=out_cstride,
+                             res_buf=res.buf if res is not None else -1, res_coff=res.start if res is not None else 0,
+                             ksize=k, stride=stride, act=act, row_off=row_off, in_mean=in_mean, in_std=in_std,
+                             w_off=self._push(wp), b_off=self._push(bp), wtc_off=-1))
+        self.names.append(name)
+        self.macs.append(ho * wo * k * k * cin * cout)
+
+    def simple(self, kind: int, name: str, src: View, dst: View, ksize: int = 1, stride: int = 1,
+               out_cstride: int = 1, w: Optional[np.ndarray] = None, b: Optional[np.ndarray] = None,
+               act: int = L.ACT_NONE) -> None:
+        n = src.phys if out_cstride == 1 else src.logical
+        w_off = self._push(w) if w is not None else 0
+        b_off = self._push(b) if b is not None else 0
+        self.ops.append(dict(kind=kind, in_buf=src.buf, in_coff=src.start, cin=n, out_buf=dst.buf, out_coff=dst.start,
+                             cout=n, out_cstride=out_cstride, res_buf=-1, res_coff=0, ksize=ksize, stride=stride,
+                             act=act, row_off=0, in_mean=0.0, in_std=1.0, w_off=w_off, b_off=b_off, wtc_off=-1))
+        self.names.append(name)
+        self.macs.append(0)
+
+    # ---- finalisation
+    def layout(self, max_batch: int) -> int:
+        """Assign workspace offsets; returns the workspace size in bytes."""
+        off = 0
+        for b in self.bufs:
+            esz = {L.FMT_SPLIT16: 2, L.FMT_F32: 4, L.FMT_U8: 1}[b["fmt"]]
+            b["image_bytes"] = b["h"] * b["w"] * b["c"] * esz
+            if b["fmt"] == L.FMT_U8:
+                b["offset"] = 0
+                continue
+            b["offset"] = off
+            planes = 2 if b["fmt"] == L.FMT_SPLIT16 else 1
+            off += planes * max_batch * b["image_bytes"]
+            off = (off + 1023) // 1024 * 1024
+        return off
+
+    def c_arrays(self):
+        bufs = (L.BufDesc * len(self.bufs))()
+        for i, b in enumerate(self.bufs):
+            bufs[i] = L.BufDesc(b["h"], b["w"], b["c"], b["fmt"], b["offset"], b["image_bytes"])
+        ops = (L.OpDesc * len(self.ops))()
+        keys = [f[0] for f in L.OpDesc._fields_]
+        for i, o in enumerate(self.ops):
+            ops[i] = L.OpDesc(*[o[k] for k in keys])
+        return bufs, ops
+
+
+# ============================================================================ detector
+def build_detector_plan(model: NcnnModel, in_size: int = 640) -> Plan:
+    P = Plan()
+    convs = list(model.convs)
+    depths = list(model.c2f_depths)
+    if len(depths) != 8:
+        raise RuntimeError(f"unsupported detector graph: expected 8 C2f blocks, found {len(depths)}")
+    it = iter(convs)
+
+    def nxt(k: int, s: int, cin: Optional[int] = None) -> ConvRec:
+        c = next(it)
+        if c.ksize != k or c.stride != s or (cin is not None and c.cin != cin):
+            raise RuntimeError(f"unsupported detector graph at {c.name}: got k{c.ksize} s{c.stride} cin{c.cin}, "
+                               f"template expects k{k} s{s} cin{cin}")
+        return c
+
+    SILU, NONE = L.ACT_SILU, L.ACT_NONE
+
+    def conv(c: ConvRec, src: View, dst: View, res=None, row_off=0, kind=L.OP_CONV):
+        P.conv(c.name, c.weight, c.bias, src, dst, c.stride, SILU if c.silu else NONE, res, row_off, kind=kind)
+
+    def c2f(src: View, n: int, dst_of) -> View:
+        """cv1 -> [a|b]; b_{i+1} = b_i + cvb(cva(b_i)); cv2(cat[a, b_0..b_n]) -> dst.
+        ``dst_of(cout)`` returns the destination view."""
+        cv1 = nxt(1, 1, src.logical)
+        c = cv1.cout // 2
+        h, w = P.bufs[src.buf]["h"], P.bufs[src.buf]["w"]
+        cat = P.new_view(h, w, [c] * (2 + n))
+        conv(cv1, src, cat.seg(0, 2))
+        for i in range(n):
+            cva, cvb = nxt(3, 1, c), nxt(3, 1, c)
+            tmp = P.new_view(h, w, [c])
+            conv(cva, cat.seg(1 + i), tmp)
+            conv(cvb, tmp, cat.seg(2 + i), res=cat.seg(1 + i))
+        cv2 = nxt(1, 1, (2 + n) * c)
+        dst = dst_of(cv2.cout)
+        conv(cv2, cat, dst)
+        return dst
+
+    S = in_size
+    img = View(P.buf(S, S, 3, L.FMT_U8), (0,), (3,), False)
+    # ---- backbone
+    c0 = nxt(3, 2, 3)
+    t0 = P.new_view(S // 2, S // 2, [c0.cout])
+    conv(c0, img, t0, kind=L.OP_STEM_U8)
+    c1 = nxt(3, 2, c0.cout)
+    t1 = P.new_view(S // 4, S // 4, [c1.cout])
+    conv(c1, t0, t1)
+    t2 = c2f(t1, depths[0], lambda co: P.new_view(S // 4, S // 4, [co]))
+    c3 = nxt(3, 2, t2.logical)
+    t3 = P.new_view(S // 8, S // 8, [c3.cout])
+    conv(c3, t2, t3)
+    # model.4 output lands in the P3 neck concat [up(model.12) | model.4]; widths are only known after
+    # walking further, so peek: model.12's width = cv2 cout of the 6th C2f.  Build lazily via placeholders.
+    # Simpler: first compute widths by a dry walk over the conv list.
+    widths = _dry_widths(convs, depths)
+    cat_p3 = P.new_view(S // 8, S // 8, [widths["m12"], widths["m4"]])      # cat_7 = [up(m12), m4]
+    cat_p4 = P.new_view(S // 16, S // 16, [widths["m9"], widths["m6"]])     # cat_5 = [up(m9), m6]
+    m4 = c2f(t3, depths[1], lambda co: cat_p3.seg(1))
+    c5 = nxt(3, 2, m4.logical)
+    t5 = P.new_view(S // 16, S // 16, [c5.cout])
+    conv(c5, m4, t5)
+    m6 = c2f(t5, depths[2], lambda co: cat_p4.seg(1))
+    c7 = nxt(3, 2, m6.logical)
+    t7 = P.new_view(S // 32, S // 32, [c7.cout])
+    conv(c7, m6, t7)
+    m8 = c2f(t7, depths[3], lambda co: P.new_view(S // 32, S // 32, [co]))
+    # ---- SPPF: cv1 -> [x | mp(x) | mp(mp(x)) | mp^3(x)] -> cv2
+    s1 = nxt(1, 1, m8.logical)
+    sp = P.new_view(S // 32, S // 32, [s1.cout] * 4)
+    conv(s1, m8, sp.seg(0))
+    for i in range(3):
+        P.simple(L.OP_MAXPOOL, f"sppf.maxpool{i}", sp.seg(i), sp.seg(i + 1), ksize=5, stride=1)
+    s2 = nxt(1, 1, 4 * s1.cout)
+    cat_p5n = P.new_view(S // 32, S // 32, [widths["m19"], s2.cout])        # cat_11 = [m19, m9]
+    m9 = cat_p5n.seg(1)
+    conv(s2, sp, m9)
+    # ---- top-down
+    P.simple(L.OP_UPSAMPLE2, "upsample.m10", m9, cat_p4.seg(0))
+    cat_p4n = P.new_view(S // 16, S // 16, [widths["m16"], widths["m12"]])  # cat_9 = [m16, m12]
+    m12 = c2f(cat_p4, depths[4], lambda co: cat_p4n.seg(1))
+    P.simple(L.OP_UPSAMPLE2, "upsample.m13", m12, cat_p3.seg(0))
+    p3 = c2f(cat_p3, depths[5], lambda co: P.new_view(S // 8, S // 8, [co]))
+    # ---- bottom-up
+    c16 = nxt(3, 2, p3.logical)
+    conv(c16, p3, cat_p4n.seg(0))
+    p4 = c2f(cat_p4n, depths[6], lambda co: P.new_view(S // 16, S // 16, [co]))
+    c19 = nxt(3, 2, p4.logical)
+    conv(c19, p4, cat_p5n.seg(0))
+    p5 = c2f(cat_p5n, depths[7], lambda co: P.new_view(S // 32, S // 32, [co]))
+    # ---- Detect: per level box (3x3, 3x3, 1x1 -> 64 raw) and cls (3x3, 3x3, 1x1 -> nc raw)
+    n_anchors = sum((S // s) ** 2 for s in (8, 16, 32))
+    head_specs = []
+    row = 0
+    for lvl, feat in enumerate((p3, p4, p5)):
+        h = P.bufs[feat.buf]["h"]
+        b0, b1, b2 = nxt(3, 1, feat.logical), nxt(3, 1), nxt(1, 1)
+        k0, k1, k2 = nxt(3, 1, feat.logical), nxt(3, 1), nxt(1, 1)
+        if b2.cout != 64 or b2.silu or k2.silu:
+            raise RuntimeError("unsupported Detect head (reg_max must be 16)")
+        head_specs.append((feat, h, (b0, b1, b2), (k0, k1, k2), row))
+        row += h * h
+    nc = head_specs[0][3][2].cout
+    hc = 64 + (nc + 3) // 4 * 4
+    # buffers for the branches first, the head buffer LAST (lp_detect_forward reads bufs.back())
+    staged = []
+    for feat, h, box, cls, row in head_specs:
+        hb1, hb2 = P.new_view(h, h, [box[0].cout]), P.new_view(h, h, [box[1].cout])
+        hc1, hc2 = P.new_view(h, h, [cls[0].cout]), P.new_view(h, h, [cls[1].cout])
+        staged.append((feat, box, cls, row, hb1, hb2, hc1, hc2))
+    head = P.buf(n_anchors, 1, hc, L.FMT_F32)
+    for feat, box, cls, row, hb1, hb2, hc1, hc2 in staged:
+        conv(box[0], feat, hb1)
+        conv(box[1], hb1, hb2)
+        conv(box[2], hb2, View(head, (0,), (64,), False), row_off=row)
+        conv(cls[0], feat, hc1)
+        conv(cls[1], hc1, hc2)
+        conv(cls[2], hc2, View(head, (64,), (nc,), False), row_off=row)
+    dfl = next(it)
+    if dfl.has_bias or dfl.cin != 16 or not np.array_equal(dfl.weight.ravel(), np.arange(16, dtype=np.float32)):
+        raise RuntimeError("unsupported Detect head: DFL projection is not arange(16)")
+    if next(it, None) is not None:
+        raise RuntimeError("unsupported detector graph: trailing convolutions")
+    P.meta.update(n_anchors=n_anchors, nc=nc, head_c=hc, in_size=S,
+                  widths=[c0.cout, c1.cout, c3.cout, c5.cout, c7.cout])
+    return P
+
+
+def _dry_widths(convs: List[ConvRec], depths: List[int]) -> Dict[str, int]:
+    """Output widths of the modules whose results are concat operands (model.4/6/9/12/16/19)."""
+    i = 2                                   # after model.0, model.1
+    out = {}
+
+    def skip_c2f(n):
+        nonlocal i
+        i += 1 + 2 * n
+        w = convs[i].cout
+        i += 1
+        return w
+
+    skip_c2f(depths[0])                     # model.2
+    i += 1                                  # model.3
+    out["m4"] = skip_c2f(depths[1])
+    i += 1                                  # model.5
+    out["m6"] = skip_c2f(depths[2])
+    i += 1                                  # model.7
+    skip_c2f(depths[3])                     # model.8
+    i += 1                                  # sppf cv1
+    out["m9"] = convs[i].cout
+    i += 1
+    out["m12"] = skip_c2f(depths[4])
+    skip_c2f(depths[5])                     # model.15
+    out["m16"] = convs[i].cout
+    i += 1
+    skip_c2f(depths[6])                     # model.18
+    out["m19"] = convs[i].cout
+    return out
+
+
+# ============================================================================ classifier
+def _fold_bn(w: np.ndarray, sd: dict, bn: str, eps: float = 1e-5):
+    g = sd[bn + ".weight"].astype(np.float64)
+    beta = sd[bn + ".bias"].astype(np.float64)
+    mu = sd[bn + ".running_mean"].astype(np.float64)
+    var = sd[bn + ".running_var"].astype(np.float64)
+    s = g / np.sqrt(var + eps)
+    return (w.astype(np.float64) * s.reshape(-1, 1, 1, 1)).astype(np.float32), (beta - mu * s).astype(np.float32)
+
+
+def build_classifier_plan(state_dict: dict, in_size: int = 64, mean: float = 0.18, std: float = 0.34) -> Plan:
+    """torchvision ShuffleNetV2 x1.0 (shufflenetv2.py) -> plan.  fp32 activations.
+    channel_shuffle(cat[a, b], 2) == a to even channels, b to odd channels: expressed as
+    stride-2 channel stores of the two producers."""
+    sd = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state_dict.items()}
+    P = Plan()
+    F32, RELU, NONE = L.FMT_F32, L.ACT_RELU, L.ACT_NONE
+    S = in_size
+    img = View(P.buf(S, S, 3, L.FMT_U8), (0,), (3,), False)
+    w, b = _fold_bn(sd["conv1.0.weight"], sd, "conv1.1")
+    h = S // 2
+    x = P.new_view(h, h, [w.shape[0]], F32)
+    P.conv("conv1", w, b, img, x, 2, RELU, kind=L.OP_STEM_U8, in_mean=mean, in_std=std)
+    h //= 2
+    y = P.new_view(h, h, [x.logical], F32)
+    P.simple(L.OP_MAXPOOL, "maxpool", x, y, ksize=3, stride=2)
+    x = y
+
+    def dw(name, prefix_conv, prefix_bn, src, stride):
+        wdw, bdw = _fold_bn(sd[prefix_conv + ".weight"], sd, prefix_bn)        # [C,1,3,3]
+        c = wdw.shape[0]
+        hs = P.bufs[src.buf]["h"]
+        ho = (hs + 2 - 3) // stride + 1
+        dst = P.new_view(ho, ho, [c], F32)
+        P.simple(L.OP_DWCONV3, name, src, dst, ksize=3, stride=stride,
+                 w=wdw.reshape(c, 9).T.copy(), b=bdw)
+        P.macs[-1] = ho * ho * 9 * c
+        return dst
+
+    def pw(name, prefix_conv, prefix_bn, src, dst, cstride=1):
+        wp, bp = _fold_bn(sd[prefix_conv + ".weight"], sd, prefix_bn)
+        P.conv(name, wp, bp, src, dst, 1, RELU, out_cstride=cstride)
+
+    stage = 2
+    while f"stage{stage}.0.branch2.0.weight" in sd:
+        u = 0
+        while f"stage{stage}.{u}.branch2.0.weight" in sd:
+            pre = f"stage{stage}.{u}"
+            cin = x.logical
+            if u == 0:                                  # down-sampling unit: both branches see all channels
+                bf = sd[pre + ".branch2.5.weight"].shape[0]
+                ho = (P.bufs[x.buf]["h"] + 2 - 3) // 2 + 1
+                out = P.new_view(ho, ho, [2 * bf], F32)
+                even = View(out.buf, (0,), (bf,), False)
+                odd = View(out.buf, (1,), (bf,), False)
+                t = dw(pre + ".branch1.dw", pre + ".branch1.0", pre + ".branch1.1", x, 2)
+                pw(pre + ".branch1.pw", pre + ".branch1.2", pre + ".branch1.3", t, even, 2)
+                t = P.new_view(P.bufs[x.buf]["h"], P.bufs[x.buf]["h"], [bf], F32)
+                pw(pre + ".branch2.pw1", pre + ".branch2.0", pre + ".branch2.1", x, t)
+                t = dw(pre + ".branch2.dw", pre + ".branch2.3", pre + ".branch2.4", t, 2)
+                pw(pre + ".branch2.pw2", pre + ".branch2.5", pre + ".branch2.6", t, odd, 2)
+            else:                                       # basic unit: x1 passes through, x2 -> branch2
+                bf = cin // 2
+                hh = P.bufs[x.buf]["h"]
+                out = P.new_view(hh, hh, [cin], F32)
+                even = View(out.buf, (0,), (bf,), False)
+                odd = View(out.buf, (1,), (bf,), False)
+                x1 = View(x.buf, (0,), (bf,), False)
+                x2 = View(x.buf, (bf,), (bf,), False)
+                P.simple(L.OP_COPY, pre + ".passthrough", x1, even, out_cstride=2)
+                t = P.new_view(hh, hh, [bf], F32)
+                pw(pre + ".branch2.pw1", pre + ".branch2.0", pre + ".branch2.1", x2, t)
+                t = dw(pre + ".branch2.dw", pre + ".branch2.3", pre + ".branch2.4", t, 1)
+                pw(pre + ".branch2.pw2", pre + ".branch2.5", pre + ".branch2.6", t, odd, 2)
+            x = out
+            u += 1
+        stage += 1
+    w5, b5 = _fold_bn(sd["conv5.0.weight"], sd, "conv5.1")
+    hh = P.bufs[x.buf]["h"]
+    y = P.new_view(hh, hh, [w5.shape[0]], F32)
+    P.conv("conv5", w5, b5, x, y, 1, RELU)
+    fcw, fcb = sd["fc.weight"], sd["fc.bias"]                       # [C, 1024]
+    P.ops.append(dict(kind=L.OP_MEAN_FC, in_buf=y.buf, in_coff=0, cin=fcw.shape[1], out_buf=-1, out_coff=0,
+                      cout=fcw.shape[0], out_cstride=1, res_buf=-1, res_coff=0, ksize=1, stride=1, act=NONE,
+                      row_off=0, in_mean=0.0, in_std=1.0, w_off=P._push(fcw.T.copy()), b_off=P._push(fcb), wtc_off=-1))
+    P.names.append("mean_fc")
+    P.macs.append(fcw.size)
+    P.meta.update(num_classes=int(fcw.shape[0]), in_size=S)
+    return P
