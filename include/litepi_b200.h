@@ -159,6 +159,11 @@ int lp_pack_records(lp_ctx* ctx, const int32_t* roi_src, const int32_t* frame_id
 /* Workspace bytes lp_detect_forward / lp_classify need for the loaded plan (0 if not loaded). */
 size_t lp_workspace_bytes(lp_ctx* ctx, int net);
 
+/* Probe: CUDA events around op `op_index` of plan `net` on the launching stream (op_index < 0
+ * disables).  lp_probe_read returns how many samples it wrote (ms each, oldest first, <= 512). */
+int lp_probe_set(lp_ctx* ctx, int net, int op_index);
+int lp_probe_read(lp_ctx* ctx, float* ms_h, int cap);
+
 /* Counters: number of kernels this library launched since lp_create (bench gpu_launches). */
 int64_t lp_launch_count(lp_ctx* ctx);
 

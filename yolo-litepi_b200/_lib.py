@@ -62,6 +62,8 @@ _PROTOS = {
     "lp_pack_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lp_launch_count": (C.c_int64, [C.c_void_p]),
+    "lp_probe_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "lp_probe_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
 }
 
 EXPORTS = tuple(_PROTOS)
@@ -106,6 +108,16 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().lp_launch_count(self._h))
+
+    def probe_set(self, net: int, op_index: int):
+        check(lib().lp_probe_set(self._h, net, op_index), "lp_probe_set")
+
+    def probe_read(self):
+        buf = (C.c_float * 512)()
+        n = lib().lp_probe_read(self._h, buf, 512)
+        if n < 0:
+            check(n, "lp_probe_read")
+        return [float(buf[i]) for i in range(n)]
 
     def set_tensor_core(self, enable: bool):
         check(lib().lp_set_tensor_core(self._h, 1 if enable else 0))

@@ -40,8 +40,30 @@ extern "C" int lp_create(lp_ctx** out, int device) {
 }
 
 extern "C" int lp_destroy(lp_ctx* ctx) {
+    if (ctx) for (cudaEvent_t e : ctx->probe_ev) cudaEventDestroy(e);
     delete ctx;
     return 0;
+}
+
+extern "C" int lp_probe_set(lp_ctx* ctx, int net, int op_index) {
+    LP_CHECK(ctx, "lp_probe_set: null ctx");
+    if (ctx->probe_ev.empty() && op_index >= 0) {
+        ctx->probe_ev.resize(2 * LP_PROBE_RING);
+        for (auto& e : ctx->probe_ev) LP_CUDA(cudaEventCreate(&e));
+    }
+    ctx->probe_net = net; ctx->probe_op = op_index; ctx->probe_n = 0;
+    return 0;
+}
+
+extern "C" int lp_probe_read(lp_ctx* ctx, float* ms_h, int cap) {
+    LP_CHECK(ctx && ms_h, "lp_probe_read: null argument");
+    const int n = ctx->probe_n < LP_PROBE_RING ? ctx->probe_n : LP_PROBE_RING;
+    int m = 0;
+    for (int i = 0; i < n && m < cap; ++i, ++m) {
+        LP_CUDA(cudaEventSynchronize(ctx->probe_ev[2 * i + 1]));
+        LP_CUDA(cudaEventElapsedTime(&ms_h[m], ctx->probe_ev[2 * i], ctx->probe_ev[2 * i + 1]));
+    }
+    return m;
 }
 
 extern "C" int lp_set_tensor_core(lp_ctx* ctx, int enable) {

@@ -57,8 +57,12 @@ struct lp_ctx {
     int64_t launches = 0;
     int use_tc = 1;
     lp_net_plan nets[2];
-    void* tmaps_dev = nullptr;      // reserved
+    // probe: CUDA events around one op of one plan (bench.py roofline of the dominant kernel)
+    int probe_net = -1, probe_op = -1;
+    std::vector<cudaEvent_t> probe_ev;   // pairs (start, stop), ring
+    int probe_n = 0;
 };
+#define LP_PROBE_RING 512
 
 // ---- split-f16 helpers -------------------------------------------------------
 __device__ __forceinline__ float split_load(const __half* hi, const __half* lo, size_t i) {
