@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded
+inputs, the committed golden vectors, and size-independent properties at BASELINE sizes.
+
+Tolerances (BASELINE.json north_star): NMS keep indices and ROI integers bit-exact given identical
+pre-NMS input; detector out0 within 1e-2 px (boxes) / 1e-3 (scores); classifier top-1 equal and
+logits within 1e-2.  Integer/byte stages (letterbox, ROI resize) are bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, debug_roi_paths, oracle_pipeline_run
+from oracle import pipeline_ref as PR
+from oracle.ncnn_graph import DetectorOracle
+
+pytestmark = pytest.mark.gpu
+
+BOX_TOL, SCORE_TOL, LOGIT_TOL = 1e-2, 1e-3, 1e-2
+
+
+@pytest.fixture(scope="module")
+def lp():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import litepi_b200
+    return litepi_b200
+
+
+@pytest.fixture(scope="module")
+def det_v1(lp, v1_paths):
+    d = lp.B200Detector(v1_paths[0], v1_paths[1], max_batch=8, seed=0)
+    orc = DetectorOracle(v1_paths[0], v1_paths[1], seed=0)
+    _sync(orc, d.model)
+    return d, orc
+
+
+@pytest.fixture(scope="module")
+def clf(lp):
+    ref = PR.build_shufflenet(49, seed=0)
+    return lp.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=ref.state_dict(), max_batch=64), ref
+
+
+def _sync(orc, model):
+    ci = iter(model.convs)
+    for ly in orc.layers:
+        if ly.type == "Convolution":
+            c = next(ci)
+            ly.weight, ly.bias = c.weight, c.bias
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("shape", [(681, 1198), (2048, 2048), (720, 1280), (480, 640), (640, 640), (333, 517),
+                                   (100, 37), (1280, 1280), (641, 639), (37, 1400), (1, 1)])
+def test_letterbox_bit_exact(det_v1, shape):
+    det, _ = det_v1
+    img = np.random.default_rng(shape[0] * 31 + shape[1]).integers(0, 256, shape + (3,), dtype=np.uint8)
+    got, r, pad = det.letterbox(img)
+    want, r2, pad2 = PR.letterbox_ref(img)
+    assert np.array_equal(got, want[:, :, ::-1])
+    assert r == r2 and pad == tuple(pad2)
+
+
+def test_letterbox_golden_and_ragged_batch(lp, det_v1):
+    det, _ = det_v1
+    from litepi_b200 import synth
+    from litepi_b200.detector import FrameBatch
+    g = np.load(os.path.join(GOLDEN, "detector_path.npz"))
+    frames = [synth.vn_frame(0), synth.tt_frame(0), synth.vn_frame(1)]          # ragged shapes in one launch
+    lb = det.letterbox_device(FrameBatch.from_host(frames, det.device)).cpu().numpy()
+    for i, name in enumerate(["vn0", "tt0", "vn1"]):
+        assert np.array_equal(lb[i, ::64, :, ::-1], g[f"{name}.lb_rows"])
+        assert det.ratio[i] == g[f"{name}.ratio_pad"][0]
+
+
+# ------------------------------------------------------------------------------------------ K2/K3
+def test_detector_forward_v1_vs_oracle_and_golden(det_v1):
+    det, orc = det_v1
+    from litepi_b200 import synth
+    frames = [synth.vn_frame(0), synth.vn_frame(1), synth.tt_frame(0)]
+    lbs = np.stack([PR.letterbox_ref(f)[0][:, :, ::-1] for f in frames])
+    got = det.forward(lbs)
+    ref = orc.forward(torch.from_numpy(lbs.astype(np.float32) / 255).permute(0, 3, 1, 2).contiguous()).numpy()
+    d = np.abs(got - ref)
+    assert d[:, :4].max() < BOX_TOL and d[:, 4].max() < SCORE_TOL
+    if det.model.convs[0].weight is not None and det_v1[0].plan.meta["widths"][0] == 8:
+        g = np.load(os.path.join(GOLDEN, "detector_path.npz"))
+        from helpers import model_paths
+        if model_paths("vntsr")[1] is not None:              # trained weights: compare with the recorded reference run
+            for i, name in enumerate(["vn0", "vn1", "tt0"]):
+                dg = np.abs(got[i] - g[f"{name}.out0"])
+                assert dg[:4].max() < BOX_TOL and dg[4].max() < SCORE_TOL
+
+
+def test_detector_forward_v2_random_weights(lp, v2_paths):
+    det = lp.B200Detector(v2_paths[0], None, max_batch=2, seed=5)
+    orc = DetectorOracle(v2_paths[0], None, seed=5)
+    _sync(orc, det.model)
+    x = np.random.default_rng(2).integers(0, 256, (2, 640, 640, 3), dtype=np.uint8)
+    got = det.forward(x)
+    ref = orc.forward(torch.from_numpy(x.astype(np.float32) / 255).permute(0, 3, 1, 2).contiguous()).numpy()
+    d = np.abs(got - ref)
+    assert d[:, :4].max() < BOX_TOL and d[:, 4].max() < SCORE_TOL
+
+
+def test_detector_batch_composition_invariant(det_v1):
+    det, _ = det_v1
+    x = np.random.default_rng(3).integers(0, 256, (5, 640, 640, 3), dtype=np.uint8)
+    a = det.forward(x)
+    b = np.concatenate([det.forward(x[i:i + 1]) for i in range(5)])
+    assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------ K4/K5
+def _check_post(det, out0, shape, r, pad, conf, iou):
+    wb, ws, wc, (cb, cs, cc, widx) = PR.postprocess_ref(out0, shape, r, pad, conf, iou, return_candidates=True)
+    gb, gs, gc = det.postprocess(out0, shape, r, pad, conf, iou)
+    assert len(gb) == len(wb)
+    assert int(det.n_cand[0]) == len(cb)
+    if len(wb) == 0:
+        assert gb.dtype == np.float64 and gb.shape == (0, 4) and gs.shape == (0,) and gc.shape == (0,)
+        return 0
+    assert gb.dtype == np.float32 and gs.dtype == np.float32 and gc.dtype == np.int64
+    assert np.array_equal(gb, wb) and np.array_equal(gs, ws) and np.array_equal(gc, wc)
+    assert np.array_equal(det.keep_idx[0, :len(gb)].cpu().numpy(), widx)
+    return len(wb)
+
+
+def test_decode_nms_bit_exact_golden(det_v1):
+    det, _ = det_v1
+    from litepi_b200 import synth
+    g = np.load(os.path.join(GOLDEN, "detector_path.npz"))
+    for name, shape in (("vn0", synth.VN_SHAPE), ("vn1", synth.VN_SHAPE), ("tt0", synth.TT_SHAPE)):
+        r, pw, ph = (float(v) for v in g[f"{name}.ratio_pad"])
+        for conf in (0.25, 0.001):
+            _check_post(det, g[f"{name}.out0"], shape, r, (pw, ph), conf, 0.45)
+            gb, gs, gc = det.postprocess(g[f"{name}.out0"], shape, r, (pw, ph), conf, 0.45)
+            tag = f"{name}.c{conf}"                                   # recorded from the reference's own postprocess
+            assert np.array_equal(gb, g[tag + ".boxes"]) and np.array_equal(gs, g[tag + ".scores"])
+
+
+@pytest.mark.parametrize("seed,n_hot,nc", [(0, 0, 1), (1, 1, 1), (2, 40, 1), (3, 900, 1), (4, 8400, 1), (5, 300, 3)])
+def test_decode_nms_bit_exact_synthetic(det_v1, seed, n_hot, nc):
+    """empty, single, dense, every-anchor (8400 candidates) and multi-class inputs"""
+    det, _ = det_v1
+    rng = np.random.default_rng(seed)
+    A = 8400
+    out0 = np.zeros((4 + nc, A), np.float32)
+    out0[0] = rng.uniform(0, 640, A); out0[1] = rng.uniform(138, 502, A)
+    out0[2] = rng.uniform(4, 200, A); out0[3] = rng.uniform(4, 200, A)
+    hot = rng.permutation(A)[:n_hot]
+    sc = rng.permutation(A * nc).astype(np.float32).reshape(nc, A) / (A * nc) * 0.2          # distinct, < 0.25
+    sc[rng.integers(0, nc, n_hot), hot] += 0.5
+    out0[4:] = sc
+    k = _check_post(det, out0, (681, 1198), 640 / 1198, (0.0, 138.0), 0.25, 0.45)
+    assert (k > 0) == (n_hot > 0)
+
+
+def test_nms_tie_order_and_idempotence(det_v1):
+    det, _ = det_v1
+    A = 64
+    out0 = np.zeros((5, A), np.float32)
+    out0[0] = 50 + 60 * (np.arange(A) % 8); out0[1] = 200 + 40 * (np.arange(A) // 8); out0[2] = 30; out0[3] = 30
+    out0[4] = 0.5                                   # all tied: defined order = higher index first
+    gb, gs, gc = det.postprocess(out0, (681, 1198), 640 / 1198, (0.0, 138.0), 0.25, 0.45)
+    _check_post(det, out0, (681, 1198), 640 / 1198, (0.0, 138.0), 0.25, 0.45)
+    kidx = det.keep_idx[0, :len(gb)].cpu().numpy()
+    assert kidx[0] == A - 1 and np.all(np.diff(kidx) < 0)
+    # idempotence: NMS of the kept set keeps everything (kept boxes pairwise iou <= thr)
+    o2 = np.zeros((5, len(gb)), np.float32)
+    o2[0] = (gb[:, 0] + gb[:, 2]) / 2; o2[1] = (gb[:, 1] + gb[:, 3]) / 2
+    o2[2] = gb[:, 2] - gb[:, 0]; o2[3] = gb[:, 3] - gb[:, 1]; o2[4] = gs
+    b2, _, _ = det.postprocess(o2, (2000, 2000), 1.0, (0.0, 0.0), 0.25, 0.45)
+    assert len(b2) == len(gb)
+
+
+# ------------------------------------------------------------------------------------------ K6
+def test_roi_resize_bit_exact(clf):
+    c, _ = clf
+    from litepi_b200 import synth
+    rng = np.random.default_rng(7)
+    crops = synth.roi_crops(70, seed=1) + [rng.integers(0, 256, s + (3,), dtype=np.uint8) for s in
+                                           [(64, 64), (10, 10), (200, 333), (64, 100), (130, 64), (500, 480), (3, 5),
+                                            (1, 1), (1, 90), (700, 2)]]
+    got = c.preprocess_batch(crops).cpu().numpy()
+    for i, cr in enumerate(crops):
+        assert np.array_equal(got[i], PR.classifier_input_ref(cr)[0]), f"crop {i} {cr.shape}"
+
+
+def test_roi_resize_reference_crops_golden(clf):
+    import cv2
+    c, _ = clf
+    paths = debug_roi_paths()
+    if not paths:
+        pytest.skip("reference debug_rois not staged")
+    g = np.load(os.path.join(GOLDEN, "classifier_input.npz"))
+    imgs = [cv2.imread(p) for p in paths]
+    got = c.preprocess_batch(imgs).cpu().numpy()
+    for i, p in enumerate(paths):
+        assert np.array_equal(got[i], g[os.path.basename(p) + ".u8"])
+
+
+def test_roi_select_bit_exact(lp, det_v1):
+    det, _ = det_v1
+    import ctypes as C
+    from litepi_b200 import _lib as L
+    from litepi_b200.detector import _ptr, _stream
+    rng = np.random.default_rng(11)
+    B, D = 3, det.max_det
+    shapes = [(681, 1198), (2048, 2048), (50, 60)]
+    counts = [37, 0, 9]
+    boxes = np.zeros((B, D, 4), np.float32)
+    for i, (h, w) in enumerate(shapes):
+        x1 = rng.uniform(-5, w + 5, D); y1 = rng.uniform(-5, h + 5, D)
+        bw = rng.choice([0.2, 3, 9, 40, 400], D); bh = rng.choice([0.2, 3, 9, 40, 400], D)
+        boxes[i] = np.clip(np.stack([x1, y1, x1 + bw, y1 + bh], 1), 0, [w, h, w, h])
+    tb = torch.from_numpy(boxes).to(det.device)
+    tc = torch.tensor(counts, dtype=torch.int32, device=det.device)
+    rx = torch.zeros((512, 4), dtype=torch.int32, device=det.device)
+    rs = torch.zeros((512, 2), dtype=torch.int32, device=det.device)
+    nr = torch.zeros((1,), dtype=torch.int32, device=det.device)
+    hh = (C.c_int32 * B)(*[s[0] for s in shapes]); ww = (C.c_int32 * B)(*[s[1] for s in shapes])
+    for min_area in (50, 100, 0):
+        L.check(L.lib().lp_roi_select(det.ctx.handle, _ptr(tb), _ptr(tc), D, hh, ww, B, min_area, 512, _ptr(rx), _ptr(rs),
+                                      _ptr(nr), _stream()))
+        want_r, want_s = [], []
+        for i in range(B):
+            rois, valid = PR.roi_select_ref(boxes[i, :counts[i]], shapes[i], min_area)
+            want_r.extend(rois.tolist()); want_s.extend([[i, k] for k in valid])
+        n = int(nr.cpu()[0])
+        assert n == len(want_r)
+        assert rx[:n].cpu().numpy().tolist() == want_r and rs[:n].cpu().numpy().tolist() == want_s
+
+
+# ------------------------------------------------------------------------------------------ K7
+def test_classifier_logits_and_top1(clf):
+    c, ref = clf
+    from litepi_b200 import synth
+    crops = synth.roi_crops(150, seed=2)                   # > max_batch: exercises chunking
+    u8 = np.stack([PR.classifier_input_ref(cr)[0] for cr in crops])
+    lg = c.logits_for(u8)
+    x = (torch.from_numpy(u8.astype(np.float32)) / 255 - 0.18) / 0.34
+    with torch.no_grad():
+        rl = ref(x.permute(0, 3, 1, 2)).numpy()
+    assert np.abs(lg - rl).max() < LOGIT_TOL
+    assert np.array_equal(lg.argmax(1), rl.argmax(1))
+    cls, probs = c.predict_batch(crops)
+    wcls, wprobs, _ = PR.classify_ref(ref, crops)
+    assert np.array_equal(cls, wcls) and np.abs(probs - wprobs).max() < 1e-4
+    assert probs.dtype == np.float32 and probs.shape == (150, 49)
+    e = c.predict_batch([])
+    assert e[0].shape == (0,) and e[1].shape == (0,)
+
+
+def test_classifier_default_init_state_dict(lp):
+    """the reference's own construction: torchvision random init + fc swap, default BatchNorm"""
+    import torch.nn as nn
+    from torchvision import models
+    torch.manual_seed(3)
+    m = models.shufflenet_v2_x1_0(weights=None)
+    m.fc = nn.Linear(m.fc.in_features, 91)
+    m.eval()
+    c = lp.B200Classifier(None, "shufflenetv2", num_classes=91, state_dict=m.state_dict(), max_batch=16)
+    u8 = np.random.default_rng(4).integers(0, 256, (16, 64, 64, 3), dtype=np.uint8)
+    x = (torch.from_numpy(u8.astype(np.float32)) / 255 - 0.18) / 0.34
+    with torch.no_grad():
+        rl = m(x.permute(0, 3, 1, 2)).numpy()
+    lg = c.logits_for(u8)
+    assert np.abs(lg - rl).max() < LOGIT_TOL and np.array_equal(lg.argmax(1), rl.argmax(1))
+
+
+# ------------------------------------------------------------------------------------------ pipeline
+def _compare(got, want):
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.abs(a["box_f32"] - b["box_f32"]).max() < BOX_TOL
+        assert abs(a["det_conf"] - b["det_conf"]) < SCORE_TOL
+        assert a["det_class"] == b["det_class"] and a["cls_class"] == b["cls_class"]
+        assert abs(a["cls_conf"] - b["cls_conf"]) < 1e-3
+
+
+def test_pipeline_vs_oracle(lp, v1_paths, clf):
+    from litepi_b200 import synth
+    _, ref = clf
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, max_batch=4,
+                           classifier_state_dict=ref.state_dict(), seed=0)
+    orc = DetectorOracle(v1_paths[0], v1_paths[1], seed=0)
+    _sync(orc, pipe.detector.model)
+    frames = [synth.vn_frame(i) for i in range(5)] + [synth.tt_frame(0)]        # 6 frames, max_batch 4: two chunks
+    got = pipe.run_batch(frames, 0.25, 0.45, 50)
+    for f, g in zip(frames, got):
+        _compare(g, oracle_pipeline_run(orc, ref, f, 0.25, 0.45, 50))
+    # reference-shaped single-frame API
+    res, m = pipe.run(frames[0], conf_threshold=0.25, iou_threshold=0.45, min_area=50)
+    want = oracle_pipeline_run(orc, ref, frames[0], 0.25, 0.45, 50)
+    assert len(res) == len(want) and m.num_detections >= len(res) and m.t_total > 0 and m.fps > 0
+    for a, b in zip(res, want):
+        assert a["bbox"] == b["bbox"] and a["cls_class"] == b["cls_class"]
+        assert set(a) == {"bbox", "det_class", "det_conf", "cls_class", "cls_conf", "time_det", "time_cls"}
+    # a frame with nothing in it
+    blank = np.full((681, 1198, 3), 127, np.uint8)
+    res, m = pipe.run(blank, 0.25, 0.45, 50)
+    assert res == [] and m.num_detections == 0
+    assert pipe.run_batch([blank], 0.25, 0.45, 50) == [[]]
+    b, s, c = pipe.detector.detect(blank, 0.25, 0.45)
+    assert b.shape == (0, 4) and b.dtype == np.float64
+
+
+def test_full_batch_properties(lp, v1_paths, clf):
+    """BASELINE configs[1] size (batch 64 VN frames): batch result == per-frame results, and the
+    gather/sort of records is a permutation-invariant of the sharding."""
+    from litepi_b200 import synth, runner
+    _, ref = clf
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, max_batch=64,
+                           classifier_state_dict=ref.state_dict(), seed=0)
+    frames = [synth.vn_frame(i) for i in range(64)]
+    whole = runner.run_sharded(pipe, frames, 0.25, 0.45, 50, 0, 1)
+    parts = np.concatenate([runner.run_sharded(pipe, frames, 0.25, 0.45, 50, r, 4) for r in range(4)])
+    parts = runner.sort_records(parts)
+    assert whole.shape == parts.shape and np.array_equal(whole, parts)
+    assert whole.shape[0] > 100
+    got = pipe.records_to_results(whole, 64)
+    one = pipe.run_batch([frames[17]], 0.25, 0.45, 50)[0]
+    assert [d["bbox"] for d in got[17]] == [d["bbox"] for d in one]
+    assert [d["cls_class"] for d in got[17]] == [d["cls_class"] for d in one]
