@@ -228,7 +228,7 @@ def main():
     pipe.ctx.probe_set(L.NET_DETECTOR, dom)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = pipe.ctx.launch_count()
+    launches0 = pipe.counters.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_rois = 0
     all_records = []
@@ -243,7 +243,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = pipe.ctx.launch_count() - launches0
+    launches = pipe.counters.launch_count() - launches0
     clocks = sampler.stop()
     probe = pipe.ctx.probe_read()
     pipe.ctx.probe_set(L.NET_DETECTOR, -1)

@@ -29,7 +29,7 @@ def lp():
 
 @pytest.fixture(scope="module")
 def det_v1(lp, v1_paths):
-    d = lp.B200Detector(v1_paths[0], v1_paths[1], max_batch=8, seed=0)
+    d = lp.B200Detector(v1_paths[0], v1_paths[1], max_batch=8, max_det=8400, seed=0)   # max_det = anchors: never truncates
     orc = DetectorOracle(v1_paths[0], v1_paths[1], seed=0)
     _sync(orc, d.model)
     return d, orc

@@ -39,7 +39,7 @@ class B200Classifier:
             raise RuntimeError("litepi_b200: no CUDA device; the B200 backend has no CPU fallback")
         self.arch, self.num_classes, self.input_size = arch, int(num_classes), int(input_size)
         self.device = torch.device("cuda", cuda_device)
-        self.ctx = L.context(cuda_device)
+        self.ctx = L.Context(cuda_device)         # one lp_ctx per classifier object
         sd = state_dict
         if sd is None:
             sd = _random_state_dict(self.num_classes, seed)

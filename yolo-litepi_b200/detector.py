@@ -73,7 +73,7 @@ class B200Detector:
         if not torch.cuda.is_available():
             raise RuntimeError("litepi_b200: no CUDA device; the B200 backend has no CPU fallback")
         self.device = torch.device("cuda", device)
-        self.ctx = L.context(device)
+        self.ctx = L.Context(device)              # one lp_ctx per detector object (it holds the plan)
         self.model = load_ncnn(param_path, bin_path, seed=seed)       # RuntimeError on failure (e2e.py:213-216)
         self.plan = build_detector_plan(self.model, self.input_size)
         self.max_batch, self.max_det = int(max_batch), int(max_det)

@@ -62,6 +62,11 @@ class B200Pipeline:
         self.device = self.detector.device
         self.ctx = self.detector.ctx
         self.max_batch = int(max_batch)
+
+        class _Launches:                      # kernels launched by both contexts (bench.py gpu_launches)
+            def __init__(s, a, b): s.a, s.b = a, b
+            def launch_count(s): return s.a.launch_count() + s.b.launch_count()
+        self.counters = _Launches(self.detector.ctx, self.classifier.ctx)
         self.max_rois = int(max_rois) if max_rois else self.max_batch * 64
         with torch.cuda.device(self.device):
             R = self.max_rois
