@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="device-resident steps only (no e2e / latency / CPU legs): the command ncu wraps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -252,6 +254,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
     value = world * B * args.steps / (ms * 1e-3)
+
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "value": value, "ms_per_step": ms / args.steps,
+                              "gpu_launches": int(launches)}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---------------- end-to-end with host frames (e2e): double-buffered pinned H2D + D2H of records
     copy_stream = torch.cuda.Stream(device=dev)

@@ -32,7 +32,8 @@ def main():
     print(torch.cuda.get_device_name(0))
     param, binp = model_paths("vntsr")
     print("weights:", "trained v1" if binp else "RANDOM (staged weights missing)")
-    det = litepi_b200.B200Detector(param, binp, max_batch=4, seed=0)
+    det = litepi_b200.B200Detector(param, binp, max_batch=4, seed=0, tensor_cores=("--simt" not in sys.argv))
+    print("tensor-core ops:", det.tc_ops)
     orc = DetectorOracle(param, binp, seed=0)
     if binp is None:
         ci = iter(det.model.convs)

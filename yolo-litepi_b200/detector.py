@@ -65,7 +65,8 @@ class B200Detector:
     def __init__(self, param_path: str, bin_path: Optional[str], input_size: int = 640,
                  use_gpu: bool = False, num_threads: int = 4,
                  input_name: str = "in0", output_name: str = "out0",
-                 device: int = 0, max_batch: int = 64, max_det: int = 1024, seed: int = 0):
+                 device: int = 0, max_batch: int = 64, max_det: int = 1024, seed: int = 0,
+                 tensor_cores: bool = True):
         # use_gpu / num_threads / input_name / output_name are accepted for signature parity with
         # NCNNDetector (e2e.py:198-200) and ignored: there is one device path.
         self.input_size = int(input_size)
@@ -80,12 +81,16 @@ class B200Detector:
         self.n_anchors = self.plan.meta["n_anchors"]
         self.nc = self.plan.meta["nc"]
         ws_bytes = self.plan.layout(self.max_batch)
+        tc_blob = self.plan.pack_tc_weights() if tensor_cores else np.zeros(0, np.uint8)
+        self.tc_ops = sum(1 for o in self.plan.ops if o["wtc_off"] >= 0)
         with torch.cuda.device(self.device):
             self.weights = torch.from_numpy(self.plan.weights()).to(self.device)
+            self.weights_tc = torch.from_numpy(tc_blob).to(self.device) if tc_blob.size else None
             self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
             bufs, ops = self.plan.c_arrays()
             L.check(L.lib().lp_net_load(self.ctx.handle, L.NET_DETECTOR, bufs, len(bufs), ops, len(ops),
-                                        _ptr(self.weights), self.weights.numel(), None, 0, self.max_batch),
+                                        _ptr(self.weights), self.weights.numel(), _ptr(self.weights_tc),
+                                        tc_blob.size, self.max_batch),
                     "lp_net_load(detector)")
             B, S, A, D = self.max_batch, self.input_size, self.n_anchors, self.max_det
             self.lb = torch.empty((B, S, S, 3), dtype=torch.uint8, device=self.device)

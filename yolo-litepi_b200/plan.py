@@ -158,6 +158,40 @@ class Plan:
             off = (off + 1023) // 1024 * 1024
         return off
 
+    def pack_tc_weights(self) -> np.ndarray:
+        """Pre-split, pre-packed tensor-core operands for every conv the tcgen05 kernel can run
+        (csrc/conv_tc.cu ``lp_conv_tc_try`` applies the same eligibility test).  Per K-block
+        (tap x <=64 input channels) the stage image is [plane hi|lo][8-channel chunk][cout][8] fp16 --
+        the UMMA K-major no-swizzle canonical layout, so one bulk copy lands a ready B operand.
+        Sets ``wtc_off`` of the eligible ops; returns the blob as uint8."""
+        W = self.weights()
+        parts, off = [], 0
+        for op in self.ops:
+            op["wtc_off"] = -1
+            if op["kind"] != L.OP_CONV or op["stride"] != 1 or op["ksize"] not in (1, 3) or op["out_cstride"] != 1:
+                continue
+            cin, cout = op["cin"], op["cout"]
+            if self.bufs[op["in_buf"]]["fmt"] != L.FMT_SPLIT16 or cin % 16 or cout % 16 or cout > 256 or cin > 512:
+                continue
+            kb = next((d for d in (64, 48, 32, 16) if cin % d == 0), 0)      # channels per K-block
+            if not kb:
+                continue
+            taps, ncb = op["ksize"] ** 2, cin // kb
+            w = W[op["w_off"]:op["w_off"] + taps * cin * cout].reshape(taps, cin, cout)
+            hi = w.astype(np.float16)
+            lo = (w - hi.astype(np.float32)).astype(np.float16)
+            planes = [a.reshape(taps, ncb, kb // 8, 8, cout).transpose(0, 1, 2, 4, 3) for a in (hi, lo)]
+            blob = np.ascontiguousarray(np.stack(planes, axis=2))        # [tap][cb][plane][chunk][cout][8]
+            raw = blob.view(np.uint8).ravel()
+            op["wtc_off"] = off
+            parts.append(raw)
+            off += raw.size
+            pad = (-off) % 128
+            if pad:
+                parts.append(np.zeros(pad, np.uint8))
+                off += pad
+        return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
     def c_arrays(self):
         bufs = (L.BufDesc * len(self.bufs))()
         for i, b in enumerate(self.bufs):
