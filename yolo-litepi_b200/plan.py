@@ -168,10 +168,12 @@ class Plan:
         parts, off = [], 0
         for op in self.ops:
             op["wtc_off"] = -1
-            if op["kind"] != L.OP_CONV or op["stride"] != 1 or op["ksize"] not in (1, 3) or op["out_cstride"] != 1:
+            if op["kind"] != L.OP_CONV or op["out_cstride"] != 1:
+                continue
+            if (op["ksize"], op["stride"]) not in ((1, 1), (3, 1), (3, 2)):
                 continue
             cin, cout = op["cin"], op["cout"]
-            if self.bufs[op["in_buf"]]["fmt"] != L.FMT_SPLIT16 or cin % 16 or cout % 16 or cout > 256 or cin > 512:
+            if self.bufs[op["in_buf"]]["fmt"] != L.FMT_SPLIT16 or cin % 16 or cout % 16 or cout > 128 or cin > 512:
                 continue
             kb = next((d for d in (64, 48, 32, 16) if cin % d == 0), 0)      # channels per K-block
             if not kb:
