@@ -164,6 +164,11 @@ size_t lp_workspace_bytes(lp_ctx* ctx, int net);
 int lp_probe_set(lp_ctx* ctx, int net, int op_index);
 int lp_probe_read(lp_ctx* ctx, float* ms_h, int cap);
 
+/* Debugging: per-role cycle counters of the tensor-core conv kernel (CTA 0) into a device buffer of
+ * 16 int64 (NULL disables): [0..2] loader wait-empty/issue/wait-copy, [3..7] MMA wait-acc/wait-patch/
+ * wait-weights/total/tiles, [8..9] epilogue wait/total. */
+int lp_debug_tc_timing(lp_ctx* ctx, void* dev_buf16);
+
 /* Counters: number of kernels this library launched since lp_create (bench gpu_launches). */
 int64_t lp_launch_count(lp_ctx* ctx);
 

@@ -62,6 +62,7 @@ _PROTOS = {
     "lp_pack_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lp_launch_count": (C.c_int64, [C.c_void_p]),
+    "lp_debug_tc_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lp_probe_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "lp_probe_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
 }

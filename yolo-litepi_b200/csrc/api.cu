@@ -45,9 +45,15 @@ extern "C" int lp_destroy(lp_ctx* ctx) {
     return 0;
 }
 
+extern "C" int lp_debug_tc_timing(lp_ctx* ctx, void* dev_buf16) {
+    LP_CHECK(ctx, "lp_debug_tc_timing: null ctx");
+    ctx->tc_dbg = (long long*)dev_buf16;
+    return 0;
+}
+
 extern "C" int lp_probe_set(lp_ctx* ctx, int net, int op_index) {
     LP_CHECK(ctx, "lp_probe_set: null ctx");
-    if (ctx->probe_ev.empty() && op_index >= 0) {
+    if (ctx->probe_ev.empty() && (op_index >= 0 || op_index == -2)) {
         ctx->probe_ev.resize(2 * LP_PROBE_RING);
         for (auto& e : ctx->probe_ev) LP_CUDA(cudaEventCreate(&e));
     }

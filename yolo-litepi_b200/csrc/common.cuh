@@ -61,6 +61,7 @@ struct lp_ctx {
     int probe_net = -1, probe_op = -1;
     std::vector<cudaEvent_t> probe_ev;   // pairs (start, stop), ring
     int probe_n = 0;
+    long long* tc_dbg = nullptr;     // device buffer (16 x int64) for conv_tc role timing; debugging only
 };
 #define LP_PROBE_RING 512
 

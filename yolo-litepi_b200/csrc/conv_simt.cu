@@ -434,13 +434,16 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
     const int net_id = (&net == &ctx->nets[0]) ? 0 : 1;
     for (size_t oi = 0; oi < net.ops.size(); ++oi) {
         const lp_op_desc& op = net.ops[oi];
-        const bool probe = (ctx->probe_net == net_id && ctx->probe_op == (int)oi && !ctx->probe_ev.empty());
-        const int slot = ctx->probe_n % LP_PROBE_RING;
+        // probe_op >= 0: ring of samples of that op; probe_op == -2: one sample of EVERY op (slot = op index)
+        const bool probe_all = (ctx->probe_net == net_id && ctx->probe_op == -2 && !ctx->probe_ev.empty() && (int)oi < LP_PROBE_RING);
+        const bool probe = probe_all || (ctx->probe_net == net_id && ctx->probe_op == (int)oi && !ctx->probe_ev.empty());
+        const int slot = probe_all ? (int)oi : ctx->probe_n % LP_PROBE_RING;
         if (probe) LP_CUDA(cudaEventRecord(ctx->probe_ev[2 * slot], st));
         struct ProbeStop {
             lp_ctx* c; bool on; int slot; cudaStream_t st;
-            ~ProbeStop() { if (on) { cudaEventRecord(c->probe_ev[2 * slot + 1], st); c->probe_n++; } }
-        } probe_stop{ctx, probe, slot, st};
+            bool all;
+            ~ProbeStop() { if (on) { cudaEventRecord(c->probe_ev[2 * slot + 1], st); if (all) { if (c->probe_n < slot + 1) c->probe_n = slot + 1; } else c->probe_n++; } }
+        } probe_stop{ctx, probe, slot, st, probe_all};
         ConvParams p{};
         const lp_buf_desc& ob = net.bufs[op.out_buf >= 0 ? op.out_buf : op.in_buf];
         p.cin = op.cin; p.cout = op.cout; p.out_cstride = op.out_cstride > 0 ? op.out_cstride : 1;

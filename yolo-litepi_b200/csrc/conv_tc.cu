@@ -1,9 +1,12 @@
 // K2: implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05, sm_100a).
 //
 // GEMM view per tile: D[128 pixels x Cout] += A[128 x K] * B[K x Cout], K = taps * Cin, fp32
-// accumulator in TMEM.  Operands are split-f16 (value = hi + lo): every K-step issues THREE
-// tcgen05.mma (Ahi*Bhi + Alo*Bhi + Ahi*Blo), which keeps ~22 mantissa bits -- single-pass
-// fp16/bf16/tf32 miss the reference's 1e-2 px box tolerance.
+// accumulator in TMEM.  Operands are split-f16 (value = hi + lo): the product keeps the three terms
+// Ahi*Bhi + Alo*Bhi + Ahi*Blo (~22 mantissa bits) -- single-pass fp16/bf16/tf32 miss the reference's
+// 1e-2 px box tolerance.  Measured on B200 (tools/ubench/mma_rate.cu) an M=128,
+// K=16 tcgen05.mma costs max(46, N/2) cycles: below N=128 it is bound by the shared-memory read of A,
+// not by N.  So each K-step issues TWO instructions instead of three: Ahi x [Bhi|Blo] (N = 2*Cout, two
+// accumulator halves) and Alo x Bhi (N = Cout); the epilogue adds the halves.
 //
 // A operand (activations): no im2col is ever materialised.  A tile stages ONE halo patch of its
 // 16x8 output pixels in shared memory, laid out [plane][8-channel chunk][patch pixel][16 B].  In the
@@ -19,18 +22,21 @@
 // Epilogue: tcgen05.ld (TMEM lane = pixel) -> bias -> act -> (+residual) -> split -> NHWC stores,
 // written at a channel offset of the destination buffer (concat / C2f views are store patterns).
 //
-// Persistent, warp-specialised CTA (320 threads, one per SM, static round-robin over tiles):
-//   warps 0-3  epilogue (TMEM quadrant = warp id)            <- acc_full / -> acc_empty
-//   warp  4    weight producer (one lane, bulk TMA)          <- w_empty   / -> w_full
-//   warp  5    TMEM allocator + MMA issuer (one lane)        <- patch_full, w_full, acc_empty
-//   warps 6-9  patch loaders (cp.async 16 B, zero-fill halo) <- patch_empty / -> patch_full
-// Two accumulator stages in TMEM and up to two patch stages let tile i+1 load and tile i-1 drain
-// while tile i is in the tensor core.
+// Persistent, warp-specialised CTA (576 threads, one per SM, static round-robin over tiles):
+//   warps 0-7   epilogue (TMEM quadrant = warp % 4, column half = warp / 4)  <- acc_full / -> acc_empty
+//   warp  8     weight producer (one lane, bulk TMA)                         <- w_empty   / -> w_full
+//   warp  9     TMEM allocator + MMA issuer (one lane)                       <- patch_full, w_full, acc_empty
+//   warps 10-17 patch loaders (cp.async 16 B, zero-fill halo)                <- patch_empty / -> patch_full
+// Up to 8 patch stages and 4 TMEM accumulator stages keep several tiles in flight: the small-channel
+// layers are HBM/latency-bound, so tiles i+1.. load and tile i-1 drains while tile i is in the tensor core.
 #include "common.cuh"
 
 namespace {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 576;
+constexpr int EPI_WARPS = 8, W_PRODUCER = 8, W_MMA = 9, W_LOADER0 = 10, LOADER_WARPS = 8;   // warp roles
+constexpr int LOADER_THREADS = LOADER_WARPS * 32;
+constexpr int MAX_PST = 8, MAX_AST = 4;    // patch / accumulator stages
 constexpr int TILE_M = 128;
 constexpr int TCT_H = 16, TCT_W = 8;       // spatial output tile (rows x cols)
 constexpr int MAX_WST = 16;                // weight stages / resident K-blocks
@@ -50,10 +56,12 @@ struct TcParams {
     int phase_slots;           // stride 2: slots per parity phase
     int kb_ch, n_cb, n_kb;     // channels per K-block, channel blocks, total K-blocks (taps * n_cb)
     int w_stages, stage_bytes, resident;
-    int patch_stages;
+    int patch_stages, acc_stages;
+    int tab_bytes;             // 3x3: per-item geometry table (py | px<<6 | chunk<<12 | slot<<18) in shared memory
     int tmem_cols, acc_stride;  // TMEM columns allocated; column stride between the two accumulator stages
     unsigned magic_chunks, magic_pitch;   // ceil(2^32 / n) for division by n_chunks / pitch
     long long total_pix;       // 1x1: n_img*H*W
+    long long* dbg;            // optional: per-role cycle counters of CTA 0 (tools/op_times.py --tc-timing)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,6 +104,26 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// descriptors passed as (lo, hi) 32-bit halves: only the low word (start address) changes between MMAs
+__device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+        "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -112,6 +140,7 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     return v;
 }
 
+#define TCLK() (p.dbg ? clock64() : 0ll)
 struct TileCoord { int img, oy0, ox0; long long pix0; };
 
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
@@ -133,29 +162,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);        // [MAX_WST]
     uint64_t* w_empty = w_full + MAX_WST;                        // [MAX_WST]
-    uint64_t* patch_full = w_empty + MAX_WST;                    // [2]
-    uint64_t* patch_empty = patch_full + 2;                      // [2]
-    uint64_t* acc_full = patch_empty + 2;                        // [2]
-    uint64_t* acc_empty = acc_full + 2;                          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* patch_full = w_empty + MAX_WST;                    // [MAX_PST]
+    uint64_t* patch_empty = patch_full + MAX_PST;                // [MAX_PST]
+    uint64_t* acc_full = patch_empty + MAX_PST;                  // [MAX_AST]
+    uint64_t* acc_empty = acc_full + MAX_AST;                    // [MAX_AST]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + MAX_AST);
     uint8_t* patch0 = smem + 512;
     const int n_chunks = p.cin >> 3;
     const uint32_t plane_bytes = (uint32_t)n_chunks * p.slots_p * 16;
     const uint32_t patch_bytes = 2 * plane_bytes;
     uint8_t* wst = patch0 + (size_t)p.patch_stages * patch_bytes;
+    uint32_t* tab = reinterpret_cast<uint32_t*>(wst + (size_t)p.w_stages * p.stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hw_in = p.H * p.W, hw_out = p.Ho * p.Wo;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&patch_full[s], 128); mbar_init(&patch_empty[s], 1);
-            mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128);
-        }
+        for (int s = 0; s < MAX_PST; ++s) { mbar_init(&patch_full[s], LOADER_THREADS); mbar_init(&patch_empty[s], 1); }
+        for (int s = 0; s < MAX_AST; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -164,52 +192,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 6) {
-        // ================= patch loaders (128 threads) =================
-        const int lt = threadIdx.x - 192;
+    if (warp >= W_LOADER0) {
+        // ================= patch loaders (256 threads) =================
+        // The loader's instruction stream is on the critical path of the small-channel layers, so the
+        // tile-independent geometry of every 16-B item is tabulated once; per tile an item costs ~15
+        // instructions (bounds test, one multiply-add, two cp.async).
+        const int lt = threadIdx.x - W_LOADER0 * 32;
         const int items_per_plane = n_chunks * p.slots;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int ps = it % p.patch_stages;
-            if (it >= p.patch_stages) mbar_wait(&patch_empty[ps], ((it / p.patch_stages) - 1) & 1);
-            const TileCoord tc = tile_coord(p, tile);
-            const uint32_t dst0 = smem_u32(patch0 + (size_t)ps * patch_bytes);
-            for (int e = lt; e < items_per_plane; e += 128) {
+        if (p.ksize == 3) {
+            for (int e = lt; e < items_per_plane; e += LOADER_THREADS) {
                 const int slot = (int)__umulhi((unsigned)e, p.magic_chunks);       // e / n_chunks
                 const int chunk = e - slot * n_chunks;
-                bool valid;
-                long long goff;                               // element offset of the pixel inside a plane
-                if (p.ksize == 1) {
-                    const long long gpix = tc.pix0 + slot;
-                    valid = gpix < p.total_pix;
-                    const int gi = valid ? (int)(gpix / hw_in) : 0;
-                    const int pin = valid ? (int)(gpix - (long long)gi * hw_in) : 0;
-                    goff = (long long)gi * p.in_img + (long long)pin * p.in_C;
+                int py, px;
+                if (p.stride == 1) {
+                    py = slot / p.pitch;
+                    px = slot - py * p.pitch;
                 } else {
-                    int py, px;
-                    if (p.stride == 1) {
-                        py = (int)__umulhi((unsigned)slot, p.magic_pitch);           // slot / pitch
-                        px = slot - py * p.pitch;
-                    } else {
-                        const int ph = slot / p.phase_slots, q = slot - ph * p.phase_slots;
-                        const int sr = (int)__umulhi((unsigned)q, p.magic_pitch), sc = q - sr * p.pitch;
-                        py = 2 * sr + (ph >> 1);
-                        px = 2 * sc + (ph & 1);
-                    }
-                    const int iy = tc.oy0 * p.stride - 1 + py, ix = tc.ox0 * p.stride - 1 + px;
-                    valid = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W);
-                    goff = (long long)tc.img * p.in_img + (valid ? ((long long)iy * p.W + ix) * p.in_C : 0);
+                    const int ph = slot / p.phase_slots, q = slot - ph * p.phase_slots;
+                    const int sr = q / p.pitch, sc = q - sr * p.pitch;
+                    py = 2 * sr + (ph >> 1);
+                    px = 2 * sc + (ph & 1);
                 }
-                const __half* src = p.in + goff + p.in_coff + chunk * 8;
-                const uint32_t dst = dst0 + ((uint32_t)chunk * p.slots_p + slot) * 16;
-                cp_async16(dst, src, valid);
-                cp_async16(dst + plane_bytes, src + p.in_plane, valid);
+                tab[e] = (uint32_t)py | ((uint32_t)px << 6) | ((uint32_t)chunk << 12) | ((uint32_t)slot << 18);
             }
-            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-            mbar_arrive(&patch_full[ps]);
+            asm volatile("bar.sync 1, %0;" ::"n"(LOADER_THREADS) : "memory");      // loaders only
         }
-    } else if (warp == 4) {
+        // Up to `depth` tiles are in flight per thread (one cp.async group each): a tile costs a full
+        // L2/HBM round trip, so the loader must not wait for tile i before issuing tile i+1.
+        const int depth = p.patch_stages - 1 < 4 ? p.patch_stages - 1 : 4;
+        int issued = 0, arrived = 0;
+        long long t_wait_empty = 0, t_issue = 0, t_wait_cp = 0;
+        const __half* in_c = p.in + p.in_coff;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int ps = issued % p.patch_stages;
+            long long t0 = TCLK();
+            if (issued >= p.patch_stages) mbar_wait(&patch_empty[ps], ((issued / p.patch_stages) - 1) & 1);
+            long long t1 = TCLK();
+            t_wait_empty += t1 - t0;
+            const TileCoord tc = tile_coord(p, tile);
+            const uint32_t dst0 = smem_u32(patch0 + (size_t)ps * patch_bytes);
+            if (p.ksize == 1) {
+                // images are contiguous (host checks in_img == H*W*C): flattened pixel index addresses directly
+                const __half* base = in_c + tc.pix0 * p.in_C;
+                const int n_valid = (int)((p.total_pix - tc.pix0) < TILE_M ? (p.total_pix - tc.pix0) : TILE_M);
+                for (int e = lt; e < items_per_plane; e += LOADER_THREADS) {
+                    const int slot = (int)__umulhi((unsigned)e, p.magic_chunks);
+                    const int chunk = e - slot * n_chunks;
+                    const bool valid = slot < n_valid;
+                    const __half* src = base + (valid ? slot * p.in_C : 0) + chunk * 8;
+                    const uint32_t dst = dst0 + ((uint32_t)chunk * p.slots_p + slot) * 16;
+                    cp_async16(dst, src, valid);
+                    cp_async16(dst + plane_bytes, src + p.in_plane, valid);
+                }
+            } else {
+                const __half* base = in_c + (long long)tc.img * p.in_img;
+                const int y_base = tc.oy0 * p.stride - 1, x_base = tc.ox0 * p.stride - 1;
+                for (int e = lt; e < items_per_plane; e += LOADER_THREADS) {
+                    const uint32_t t = tab[e];
+                    const int iy = y_base + (int)(t & 63), ix = x_base + (int)((t >> 6) & 63);
+                    const uint32_t chunk = (t >> 12) & 63, slot = t >> 18;
+                    const bool valid = ((unsigned)iy < (unsigned)p.H) && ((unsigned)ix < (unsigned)p.W);
+                    const __half* src = base + (valid ? (iy * p.W + ix) * p.in_C : 0) + chunk * 8;
+                    const uint32_t dst = dst0 + (chunk * p.slots_p + slot) * 16;
+                    cp_async16(dst, src, valid);
+                    cp_async16(dst + plane_bytes, src + p.in_plane, valid);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ++issued;
+            long long t2 = TCLK();
+            t_issue += t2 - t1;
+            if (issued - arrived > depth) {
+                switch (depth) {
+                    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+                    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+                    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+                    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+                    default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(&patch_full[arrived % p.patch_stages]);
+                ++arrived;
+                t_wait_cp += TCLK() - t2;
+            }
+        }
+        if (p.dbg && blockIdx.x == 0 && lt == 0) { p.dbg[0] = t_wait_empty; p.dbg[1] = t_issue; p.dbg[2] = t_wait_cp; }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (; arrived < issued; ++arrived) mbar_arrive(&patch_full[arrived % p.patch_stages]);
+    } else if (warp == W_PRODUCER) {
         // ================= weight producer (bulk TMA) =================
         if (lane == 0) {
             int g = 0;                                        // running K-block counter across tiles
@@ -223,63 +294,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        // The WHOLE warp runs this loop with warp-uniform values (so the compiler keeps descriptors in
+        // uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.  The issuing thread's
+        // instruction stream is the critical path for the small-channel layers, so everything that does
+        // not depend on the tile is hoisted.
+        {
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * p.cout) >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             const uint32_t lbo_a = (uint32_t)p.slots_p * 16, sbo_a = (uint32_t)p.pitch * 16;
-            const uint32_t lbo_b = (uint32_t)p.cout * 16, sbo_b = 128;
-            const uint32_t wst_s = smem_u32(wst);
-            const uint32_t b_plane = (uint32_t)p.kb_ch * p.cout * 2;              // bytes of one plane inside a stage
+            const uint32_t lbo_b = (uint32_t)p.cout * 32, sbo_b = 128;            // chunk stride = [hi|lo] rows
+            const uint64_t da_base = umma_desc(0, lbo_a, sbo_a), db_base = umma_desc(0, lbo_b, sbo_b);
+            const uint32_t da_hi = (uint32_t)(da_base >> 32), da_lo0 = (uint32_t)da_base;
+            const uint32_t db_hi = (uint32_t)(db_base >> 32), db_lo0 = (uint32_t)db_base;
+            const uint32_t wst16 = smem_u32(wst) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4;
+            const uint32_t plane16 = plane_bytes >> 4;
+            const uint32_t a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
+            const uint32_t patch016 = smem_u32(patch0) >> 4, patch_stride16 = patch_bytes >> 4;
+            const int ksteps = p.kb_ch >> 4;
+            const bool leader = elect_one();
             int it = 0, g = 0;
+            long long m_wait_acc = 0, m_wait_patch = 0, m_wait_w = 0, m_total0 = TCLK();
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                const int ps = it % p.patch_stages, as = it & 1;
-                if (it >= 2) mbar_wait(&acc_empty[as], ((it >> 1) - 1) & 1);
+                const int ps = it % p.patch_stages, as = it % p.acc_stages;
+                long long t0 = TCLK();
+                if (it >= p.acc_stages) mbar_wait(&acc_empty[as], ((it / p.acc_stages) - 1) & 1);
+                long long t1 = TCLK();
                 mbar_wait(&patch_full[ps], (it / p.patch_stages) & 1);
+                long long t2 = TCLK();
+                m_wait_acc += t1 - t0; m_wait_patch += t2 - t1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t patch_s = smem_u32(patch0 + (size_t)ps * patch_bytes);
+                const uint32_t patch16 = da_lo0 + patch016 + (uint32_t)ps * patch_stride16;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
                 uint32_t acc = 0;
+                int cb = 0, ky = 0, kx = 0;
                 for (int kb = 0; kb < p.n_kb; ++kb, ++g) {
                     const int s = p.resident ? kb : g % p.w_stages;
                     if (!p.resident || it == 0) {
+                        long long t3 = TCLK();
                         mbar_wait(&w_full[s], p.resident ? 0 : (g / p.w_stages) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        m_wait_w += TCLK() - t3;
                     }
-                    const int tap = kb / p.n_cb, cb = kb - tap * p.n_cb;
-                    int tap_slot = 0;
+                    uint32_t tap_slot = 0;
                     if (p.ksize == 3) {
-                        const int ky = tap / 3, kx = tap - ky * 3;
                         if (p.stride == 1) tap_slot = ky * p.pitch + kx;
                         else tap_slot = ((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1);
                     }
-                    const uint32_t a_hi = patch_s + ((uint32_t)(cb * (p.kb_ch >> 3)) * p.slots_p + tap_slot) * 16;
-                    const uint32_t a_lo = a_hi + plane_bytes;
-                    const uint32_t b_hi = wst_s + (uint32_t)s * p.stage_bytes;
-                    const uint32_t b_lo = b_hi + b_plane;
-                    for (int ks = 0; ks < (p.kb_ch >> 4); ++ks) {
-                        const uint32_t ao = (uint32_t)ks * 2 * lbo_a, bo = (uint32_t)ks * 2 * lbo_b;
-                        const uint64_t dah = umma_desc(a_hi + ao, lbo_a, sbo_a), dal = umma_desc(a_lo + ao, lbo_a, sbo_a);
-                        const uint64_t dbh = umma_desc(b_hi + bo, lbo_b, sbo_b), dbl = umma_desc(b_lo + bo, lbo_b, sbo_b);
-                        umma_f16(d_tmem, dah, dbh, idesc, acc);
-                        acc = 1;
-                        umma_f16(d_tmem, dal, dbh, idesc, 1);
-                        umma_f16(d_tmem, dah, dbl, idesc, 1);
+                    uint32_t a16 = patch16 + (uint32_t)(cb * (p.kb_ch >> 3)) * p.slots_p + tap_slot;
+                    uint32_t b16 = db_lo0 + wst16 + (uint32_t)s * stage16;
+                    if (leader) {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            umma_f16_lh(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc);             // Ahi x [Bhi|Blo]
+                            umma_f16_lh(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1);     // Alo x Bhi
+                            acc = 1;
+                            a16 += a_step16;
+                            b16 += b_step16;
+                        }
+                        if (!p.resident) umma_commit(&w_empty[s]);   // frees the weight stage once these MMAs retire
                     }
-                    if (!p.resident) umma_commit(&w_empty[s]);   // frees the weight stage once these MMAs retire
+                    acc = 1;
+                    if (++cb == p.n_cb) { cb = 0; if (++kx == 3) { kx = 0; ++ky; } }
                 }
-                umma_commit(&patch_empty[ps]);
-                umma_commit(&acc_full[as]);
+                if (leader) {
+                    umma_commit(&patch_empty[ps]);
+                    umma_commit(&acc_full[as]);
+                }
+                __syncwarp();
+            }
+            if (p.dbg && blockIdx.x == 0 && leader) {
+                p.dbg[3] = m_wait_acc; p.dbg[4] = m_wait_patch; p.dbg[5] = m_wait_w; p.dbg[6] = TCLK() - m_total0; p.dbg[7] = it;
             }
         }
     } else {
-        // ================= epilogue (warps 0-3) =================
+        // ================= epilogue (warps 0-7) =================
+        const int quad = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half
+        const int c_split = (((p.cout >> 4) + 1) >> 1) << 4;   // 16-column groups: first ceil(n/2) to half 0, rest to half 1
+        const int c_begin = half ? c_split : 0, c_end = half ? p.cout : c_split;
         int it = 0;
+        long long e_wait = 0, e_total0 = TCLK();
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
+            const int as = it % p.acc_stages;
             const TileCoord tc = tile_coord(p, tile);
-            const int r = warp * 32 + lane;                  // accumulator row == TMEM lane == tile pixel
+            const int r = quad * 32 + lane;                  // accumulator row == TMEM lane == tile pixel
             bool valid;
             int oimg, opin;                                  // image and pixel-in-image of this row
             if (p.ksize == 1) {
@@ -295,64 +393,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
             const long long obase = (long long)oimg * p.out_img + (long long)opin * p.out_C + p.out_coff;
             const long long rbase = (long long)oimg * p.res_img + (long long)opin * p.res_C + p.res_coff;
-            mbar_wait(&acc_full[as], (it >> 1) & 1);
+            { long long t0 = TCLK();
+              mbar_wait(&acc_full[as], (it / p.acc_stages) & 1);
+              e_wait += TCLK() - t0; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * p.acc_stride);
-            for (int c0 = 0; c0 < p.cout; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + c0, v);
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.acc_stride);
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                uint32_t v[16], v2[16];
+                tmem_ld16(trow + c0, v);                       // Ahi*Bhi + Alo*Bhi
+                tmem_ld16(trow + p.cout + c0, v2);             // Ahi*Blo
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (!valid) continue;
+                float f[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int cc = c0 + 8 * h;
-                    float f[8];
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cc));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cc + 4));
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * q));
+                    f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + __uint_as_float(v2[4 * q + 0]) + b.x;
+                    f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + __uint_as_float(v2[4 * q + 1]) + b.y;
+                    f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + __uint_as_float(v2[4 * q + 2]) + b.z;
+                    f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + __uint_as_float(v2[4 * q + 3]) + b.w;
+                }
+                if (p.act == LP_ACT_SILU) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = act_fn(__uint_as_float(v[8 * h + i]) + bb[i], p.act);
-                    if (p.res) {
-                        const uint4 rh = *reinterpret_cast<const uint4*>(p.res + rbase + cc);
-                        const uint4 rl = *reinterpret_cast<const uint4*>(p.res + p.res_plane + rbase + cc);
+                    for (int i = 0; i < 16; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
+                } else if (p.act == LP_ACT_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
+                if (p.res) {
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        const uint4 rh = *reinterpret_cast<const uint4*>(p.res + rbase + c0 + 8 * h8);
+                        const uint4 rl = *reinterpret_cast<const uint4*>(p.res + p.res_plane + rbase + c0 + 8 * h8);
                         const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
                         const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float2 a = __half22float2(h2[i]), b = __half22float2(l2[i]);
-                            f[2 * i] += a.x + b.x;
-                            f[2 * i + 1] += a.y + b.y;
+                            f[8 * h8 + 2 * i] += a.x + b.x;
+                            f[8 * h8 + 2 * i + 1] += a.y + b.y;
                         }
                     }
-                    if (p.out_fmt == LP_FMT_SPLIT16) {
-                        uint4 oh, ol;
-                        __half2* h2 = reinterpret_cast<__half2*>(&oh);
-                        __half2* l2 = reinterpret_cast<__half2*>(&ol);
+                }
+                if (p.out_fmt == LP_FMT_SPLIT16) {
+                    uint4 oh[2], ol[2];
+                    __half2* h2 = reinterpret_cast<__half2*>(oh);
+                    __half2* l2 = reinterpret_cast<__half2*>(ol);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            __half a0, a1, b0h, b1h;
-                            split_make(f[2 * i], a0, b0h);
-                            split_make(f[2 * i + 1], a1, b1h);
-                            h2[i] = __halves2half2(a0, a1);
-                            l2[i] = __halves2half2(b0h, b1h);
-                        }
-                        __half* o = reinterpret_cast<__half*>(p.out) + obase + cc;
-                        *reinterpret_cast<uint4*>(o) = oh;
-                        *reinterpret_cast<uint4*>(o + p.out_plane) = ol;
-                    } else {
-                        float* o = reinterpret_cast<float*>(p.out) + obase + cc;
-                        *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                        *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                    for (int i = 0; i < 8; ++i) {            // packed split: hi = rn(v), lo = rn(v - hi)
+                        const __half2 hi = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                        const float2 hf = __half22float2(hi);
+                        h2[i] = hi;
+                        l2[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
                     }
+                    __half* o = reinterpret_cast<__half*>(p.out) + obase + c0;
+                    *reinterpret_cast<uint4*>(o) = oh[0];
+                    *reinterpret_cast<uint4*>(o + 8) = oh[1];
+                    *reinterpret_cast<uint4*>(o + p.out_plane) = ol[0];
+                    *reinterpret_cast<uint4*>(o + p.out_plane + 8) = ol[1];
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out) + obase + c0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(o + 4 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[as]);
         }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 5) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
@@ -385,6 +498,7 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
         p.res = reinterpret_cast<const __half*>(ws + rb.offset);
         p.res_img = rb.image_bytes / 2; p.res_plane = (long long)net.max_batch * p.res_img; p.res_C = rb.c; p.res_coff = op.res_coff;
     }
+    p.dbg = ctx->tc_dbg;
     p.wtc = net.weights_tc + op.wtc_off;
     p.bias = net.weights + op.b_off;
     p.cin = op.cin; p.cout = op.cout; p.act = op.act;
@@ -405,26 +519,33 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
     p.magic_pitch = magic_u32(p.pitch);
     p.stage_bytes = p.kb_ch * p.cout * 4;                            // 2 planes x kb_ch x cout x 2 B
     const size_t patch_bytes = (size_t)2 * (op.cin / 8) * p.slots_p * 16;
-    const size_t budget = 220 * 1024 - 512;
+    p.tab_bytes = op.ksize == 3 ? ((op.cin / 8) * p.slots * 4 + 127) / 128 * 128 : 0;
+    if (op.ksize == 1 && ib.image_bytes != (int64_t)ib.h * ib.w * ib.c * 2) return 0;
+    const size_t budget = 220 * 1024 - 512 - p.tab_bytes;
     const size_t w_all = (size_t)p.n_kb * p.stage_bytes;
-    // preference: 2 patch stages + resident weights > 2 patch stages + >=2 streaming stages > 1 patch stage
+    // weights resident if the whole layer fits beside >= 2 patch stages, else a streaming ring; the rest of
+    // shared memory goes to patch stages (deep prefetch: the small-channel layers are latency/HBM-bound)
     p.patch_stages = 0;
-    for (int ps = 2; ps >= 1 && !p.patch_stages; --ps) {
-        if (ps * patch_bytes > budget) continue;
-        const size_t left = budget - ps * patch_bytes;
-        if (w_all <= left && p.n_kb <= MAX_WST) { p.patch_stages = ps; p.resident = 1; p.w_stages = p.n_kb; }
-        else if (left >= 2 * (size_t)p.stage_bytes) {
-            p.patch_stages = ps; p.resident = 0;
-            int s = (int)(left / p.stage_bytes);
-            p.w_stages = s > 4 ? 4 : s;
-            if (p.w_stages > p.n_kb) p.w_stages = p.n_kb;
-        }
+    if (w_all + 2 * patch_bytes <= budget && p.n_kb <= MAX_WST) { p.resident = 1; p.w_stages = p.n_kb; }
+    else {
+        p.resident = 0;
+        const int min_ps = (2 * patch_bytes + 2 * (size_t)p.stage_bytes <= budget) ? 2 : 1;
+        if (min_ps * patch_bytes + 2 * (size_t)p.stage_bytes > budget) return 0;
+        int s = (int)((budget - min_ps * patch_bytes) / p.stage_bytes);
+        p.w_stages = s > 4 ? 4 : s;
+        if (p.w_stages > p.n_kb) p.w_stages = p.n_kb;
     }
-    if (!p.patch_stages) return 0;
-    p.acc_stride = op.cout < 32 ? 32 : op.cout;
+    {
+        const size_t left = budget - (size_t)p.w_stages * p.stage_bytes;
+        int ps = (int)(left / patch_bytes);
+        p.patch_stages = ps > MAX_PST ? MAX_PST : ps;
+        if (p.patch_stages < 1) return 0;
+    }
+    p.acc_stride = 2 * op.cout < 32 ? 32 : 2 * op.cout;        // [Ahi*Bhi+Alo*Bhi | Ahi*Blo]
+    p.acc_stages = 512 / p.acc_stride > MAX_AST ? MAX_AST : 512 / p.acc_stride;
     p.tmem_cols = 32;
-    while (p.tmem_cols < 2 * p.acc_stride) p.tmem_cols <<= 1;
-    const size_t smem = 512 + (size_t)p.patch_stages * patch_bytes + (size_t)p.w_stages * p.stage_bytes;
+    while (p.tmem_cols < p.acc_stages * p.acc_stride) p.tmem_cols <<= 1;
+    const size_t smem = 512 + (size_t)p.patch_stages * patch_bytes + (size_t)p.w_stages * p.stage_bytes + p.tab_bytes;
 
     if (op.ksize == 1) {
         p.total_pix = (long long)batch * ib.h * ib.w;

@@ -55,9 +55,12 @@ class B200Pipeline:
         self.detector = B200Detector(detector_param, detector_bin, input_size=det_input_size,
                                      use_gpu=use_gpu_detector, num_threads=detector_threads,
                                      device=device, max_batch=max_batch, max_det=max_det, seed=seed or 0)
+        # classify all ROIs of a frame batch in one pass: the classifier is launch/latency-bound, so its
+        # time barely depends on the ROI count (workspace = 0.77 MB per ROI slot)
         self.classifier = B200Classifier(classifier_path, classifier_arch, num_classes=num_classes,
                                          input_size=cls_input_size, device=classifier_device,
-                                         state_dict=classifier_state_dict, cuda_device=device, seed=seed)
+                                         state_dict=classifier_state_dict, cuda_device=device, seed=seed,
+                                         max_batch=min(max(256, 16 * int(max_batch)), 1024))
         self.batch_size = batch_size          # reference's classifier mini-batch; ROIs are classified in one pass here
         self.device = self.detector.device
         self.ctx = self.detector.ctx

@@ -161,7 +161,7 @@ class Plan:
     def pack_tc_weights(self) -> np.ndarray:
         """Pre-split, pre-packed tensor-core operands for every conv the tcgen05 kernel can run
         (csrc/conv_tc.cu ``lp_conv_tc_try`` applies the same eligibility test).  Per K-block
-        (tap x <=64 input channels) the stage image is [plane hi|lo][8-channel chunk][cout][8] fp16 --
+        (tap x <=64 input channels) the stage image is [8-channel chunk][plane hi|lo][cout][8] fp16 --
         the UMMA K-major no-swizzle canonical layout, so one bulk copy lands a ready B operand.
         Sets ``wtc_off`` of the eligible ops; returns the blob as uint8."""
         W = self.weights()
@@ -183,7 +183,7 @@ class Plan:
             hi = w.astype(np.float16)
             lo = (w - hi.astype(np.float32)).astype(np.float16)
             planes = [a.reshape(taps, ncb, kb // 8, 8, cout).transpose(0, 1, 2, 4, 3) for a in (hi, lo)]
-            blob = np.ascontiguousarray(np.stack(planes, axis=2))        # [tap][cb][plane][chunk][cout][8]
+            blob = np.ascontiguousarray(np.stack(planes, axis=3))        # [tap][cb][chunk][plane][cout][8]
             raw = blob.view(np.uint8).ravel()
             op["wtc_off"] = off
             parts.append(raw)
