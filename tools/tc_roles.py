@@ -35,4 +35,4 @@ for nm in names:
     t = max(int(d[7]), 1)
     print(f"{nm:8s} tiles/CTA {t:3d} | loader/tile: wait_empty {d[0]/t:7.0f} issue {d[1]/t:7.0f} wait_cp {d[2]/t:7.0f} | "
           f"MMA/tile: wait_acc {d[3]/t:7.0f} wait_patch {d[4]/t:7.0f} wait_w {d[5]/t:7.0f} total {d[6]/t:7.0f} | "
-          f"epi/tile: wait {d[8]/t:7.0f} total {d[9]/t:7.0f}  (cycles)")
+          f"epi/tile: wait {d[8]/t:6.0f} total {d[9]/t:6.0f} p1 {d[10]/t:6.0f} bar {d[11]/t:6.0f} p2 {d[12]/t:6.0f}")

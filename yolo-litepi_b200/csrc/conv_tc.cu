@@ -30,6 +30,7 @@
 // Up to 8 patch stages and 4 TMEM accumulator stages keep several tiles in flight: the small-channel
 // layers are HBM/latency-bound, so tiles i+1.. load and tile i-1 drains while tile i is in the tensor core.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -57,10 +58,14 @@ struct TcParams {
     int kb_ch, n_cb, n_kb;     // channels per K-block, channel blocks, total K-blocks (taps * n_cb)
     int w_stages, stage_bytes, resident;
     int patch_stages, acc_stages;
+    int n_mma, mtab_bytes;     // MMA issue table: one uint2 per tcgen05.mma of a tile
+    int fills_per_tile;        // streaming weights: n_kb / w_stages (stage pattern repeats every tile)
+    int epi_pitch, epi_bytes;  // epilogue staging: bytes per pixel row (+16 pad) and total (0 = direct stores)
     int tab_bytes;             // 3x3: per-item geometry table (py | px<<6 | chunk<<12 | slot<<18) in shared memory
     int tmem_cols, acc_stride;  // TMEM columns allocated; column stride between the two accumulator stages
     unsigned magic_chunks, magic_pitch;   // ceil(2^32 / n) for division by n_chunks / pitch
     long long total_pix;       // 1x1: n_img*H*W
+    int dbg_flags;             // debugging (env LP_TC_DEBUG): 1 = loaders skip copies, 2 = epilogue skips math/stores, 4 = weights loaded once
     long long* dbg;            // optional: per-role cycle counters of CTA 0 (tools/op_times.py --tc-timing)
 };
 
@@ -114,6 +119,20 @@ __device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint
         "setp.ne.b32 p, %6, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
         "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same, executed by the whole warp: only the lane with issue != 0 issues the instruction (no divergent
+// branch around it, so the surrounding loop stays in the uniform datapath).
+__device__ __forceinline__ void umma_f16_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t issue) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+        "r"(idesc), "r"(accumulate), "r"(issue)
         : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -173,6 +192,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     const uint32_t patch_bytes = 2 * plane_bytes;
     uint8_t* wst = patch0 + (size_t)p.patch_stages * patch_bytes;
     uint32_t* tab = reinterpret_cast<uint32_t*>(wst + (size_t)p.w_stages * p.stage_bytes);
+    uint2* mtab = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(tab) + p.tab_bytes);
+    uint8_t* epi = reinterpret_cast<uint8_t*>(mtab) + p.mtab_bytes;     // [plane][128 rows][epi_pitch] + row bases
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hw_in = p.H * p.W, hw_out = p.Ho * p.Wo;
@@ -226,12 +247,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int ps = issued % p.patch_stages;
             long long t0 = TCLK();
-            if (issued >= p.patch_stages) mbar_wait(&patch_empty[ps], ((issued / p.patch_stages) - 1) & 1);
+            if (issued >= p.patch_stages) {
+                // about to (possibly) block on a stage the MMA warp still reads: first publish every tile that
+                // is in flight, or the MMA warp would wait for a patch that has long landed
+                if (arrived < issued) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    for (; arrived < issued; ++arrived) mbar_arrive(&patch_full[arrived % p.patch_stages]);
+                }
+                mbar_wait(&patch_empty[ps], ((issued / p.patch_stages) - 1) & 1);
+            }
             long long t1 = TCLK();
             t_wait_empty += t1 - t0;
             const TileCoord tc = tile_coord(p, tile);
             const uint32_t dst0 = smem_u32(patch0 + (size_t)ps * patch_bytes);
-            if (p.ksize == 1) {
+            if (p.dbg_flags & 1) {
+            } else if (p.ksize == 1) {
                 // images are contiguous (host checks in_img == H*W*C): flattened pixel index addresses directly
                 const __half* base = in_c + tc.pix0 * p.in_C;
                 const int n_valid = (int)((p.total_pix - tc.pix0) < TILE_M ? (p.total_pix - tc.pix0) : TILE_M);
@@ -289,6 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 for (int kb = 0; kb < p.n_kb; ++kb, ++g) {
                     const int s = g % p.w_stages;
                     if (g >= p.w_stages) mbar_wait(&w_empty[s], ((g / p.w_stages) - 1) & 1);
+                    if ((p.dbg_flags & 4) && g >= p.w_stages) { mbar_arrive(&w_full[s]); continue; }
                     mbar_expect_tx(&w_full[s], (uint32_t)p.stage_bytes);
                     bulk_g2s(wst + (size_t)s * p.stage_bytes, p.wtc + (size_t)kb * p.stage_bytes, (uint32_t)p.stage_bytes, &w_full[s]);
                 }
@@ -296,10 +328,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         }
     } else if (warp == W_MMA) {
         // ================= MMA issuer =================
-        // The WHOLE warp runs this loop with warp-uniform values (so the compiler keeps descriptors in
-        // uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.  The issuing thread's
-        // instruction stream is the critical path for the small-channel layers, so everything that does
-        // not depend on the tile is hoisted.
+        // The whole warp runs this loop with warp-uniform values (uniform datapath); one elected lane
+        // issues.  Measured: a dependent scalar instruction costs ~6 cycles with a single warp and a
+        // tcgen05.mma ~46-64, so the loop body between two MMAs must be a handful of uniform adds.  The
+        // operand addresses of a tile are two arithmetic progressions: for each tap, A starts at
+        // patch + tap_offset and advances 2*LBO per K-step; B advances 2*LBO_B per K-step through the
+        // (contiguous) weight stages.
         {
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * p.cout) >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
@@ -307,14 +341,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             const uint32_t lbo_b = (uint32_t)p.cout * 32, sbo_b = 128;            // chunk stride = [hi|lo] rows
             const uint64_t da_base = umma_desc(0, lbo_a, sbo_a), db_base = umma_desc(0, lbo_b, sbo_b);
             const uint32_t da_hi = (uint32_t)(da_base >> 32), da_lo0 = (uint32_t)da_base;
-            const uint32_t db_hi = (uint32_t)(db_base >> 32), db_lo0 = (uint32_t)db_base;
-            const uint32_t wst16 = smem_u32(wst) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4;
+            const uint32_t db_hi = (uint32_t)(db_base >> 32);
+            const uint32_t b016 = (uint32_t)db_base + (smem_u32(wst) >> 4);
             const uint32_t plane16 = plane_bytes >> 4;
             const uint32_t a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
-            const uint32_t patch016 = smem_u32(patch0) >> 4, patch_stride16 = patch_bytes >> 4;
-            const int ksteps = p.kb_ch >> 4;
-            const bool leader = elect_one();
-            int it = 0, g = 0;
+            const uint32_t b_wrap16 = (uint32_t)p.w_stages * ((uint32_t)p.stage_bytes >> 4);
+            const uint32_t patch016 = da_lo0 + (smem_u32(patch0) >> 4), patch_stride16 = patch_bytes >> 4;
+            const int ksteps = p.kb_ch >> 4, ktot = p.cin >> 4, taps = p.ksize * p.ksize;
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            (void)mtab;
+            int it = 0;
+            uint32_t fill = 0;                              // streaming: K-blocks consumed so far (all tiles)
             long long m_wait_acc = 0, m_wait_patch = 0, m_wait_w = 0, m_total0 = TCLK();
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int ps = it % p.patch_stages, as = it % p.acc_stages;
@@ -325,37 +362,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 long long t2 = TCLK();
                 m_wait_acc += t1 - t0; m_wait_patch += t2 - t1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t patch16 = da_lo0 + patch016 + (uint32_t)ps * patch_stride16;
+                const uint32_t patch16 = patch016 + (uint32_t)ps * patch_stride16;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
                 uint32_t acc = 0;
-                int cb = 0, ky = 0, kx = 0;
-                for (int kb = 0; kb < p.n_kb; ++kb, ++g) {
-                    const int s = p.resident ? kb : g % p.w_stages;
-                    if (!p.resident || it == 0) {
-                        long long t3 = TCLK();
-                        mbar_wait(&w_full[s], p.resident ? 0 : (g / p.w_stages) & 1);
+                if (p.resident) {
+                    if (it == 0) {                          // the whole layer lands once
+                        for (int kb = 0; kb < p.n_kb; ++kb) mbar_wait(&w_full[kb], 0);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        m_wait_w += TCLK() - t3;
                     }
-                    uint32_t tap_slot = 0;
-                    if (p.ksize == 3) {
-                        if (p.stride == 1) tap_slot = ky * p.pitch + kx;
-                        else tap_slot = ((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1);
-                    }
-                    uint32_t a16 = patch16 + (uint32_t)(cb * (p.kb_ch >> 3)) * p.slots_p + tap_slot;
-                    uint32_t b16 = db_lo0 + wst16 + (uint32_t)s * stage16;
-                    if (leader) {
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            umma_f16_lh(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc);             // Ahi x [Bhi|Blo]
-                            umma_f16_lh(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1);     // Alo x Bhi
+                    uint32_t b16 = b016;
+                    uint32_t trow = 0;                      // tap row offset (ky * pitch) / phase offset
+                    for (int tap = 0; tap < taps; ++tap) {
+                        uint32_t a16 = patch16;
+                        if (p.ksize == 3) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            a16 += (p.stride == 1) ? (uint32_t)(ky * p.pitch + kx)
+                                                   : (uint32_t)(((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1));
+                        }
+                        for (int kk = 0; kk < ktot; ++kk) {
+                            umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);           // Ahi x [Bhi|Blo]
+                            umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);   // Alo x Bhi
                             acc = 1;
                             a16 += a_step16;
                             b16 += b_step16;
                         }
-                        if (!p.resident) umma_commit(&w_empty[s]);   // frees the weight stage once these MMAs retire
                     }
-                    acc = 1;
-                    if (++cb == p.n_cb) { cb = 0; if (++kx == 3) { kx = 0; ++ky; } }
+                    (void)trow;
+                } else {
+                    uint32_t b16 = b016 + (fill % (uint32_t)p.w_stages) * ((uint32_t)p.stage_bytes >> 4);
+                    for (int tap = 0; tap < taps; ++tap) {
+                        uint32_t a16 = patch16;
+                        if (p.ksize == 3) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            a16 += (p.stride == 1) ? (uint32_t)(ky * p.pitch + kx)
+                                                   : (uint32_t)(((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1));
+                        }
+                        for (int cb = 0; cb < p.n_cb; ++cb, ++fill) {
+                            const uint32_t st = fill % (uint32_t)p.w_stages;
+                            long long t3 = TCLK();
+                            mbar_wait(&w_full[st], (fill / (uint32_t)p.w_stages) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            m_wait_w += TCLK() - t3;
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);
+                                umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);
+                                acc = 1;
+                                a16 += a_step16;
+                                b16 += b_step16;
+                            }
+                            if (leader) umma_commit(&w_empty[st]);      // frees the weight stage once these MMAs retire
+                            if (st + 1 == (uint32_t)p.w_stages) b16 -= b_wrap16;
+                        }
+                    }
                 }
                 if (leader) {
                     umma_commit(&patch_empty[ps]);
@@ -369,11 +427,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         }
     } else {
         // ================= epilogue (warps 0-7) =================
+        // Phase 1 (thread = accumulator row, warp half = column half): TMEM -> bias/act/residual -> split ->
+        // staging tile in shared memory [plane][row][epi_pitch].  Phase 2: all 256 threads copy the staged
+        // tile to global with consecutive threads on consecutive 16-B chunks, so a warp store covers whole
+        // pixel rows (4-8 cache lines) instead of 32 scattered 16-B pieces.
         const int quad = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half
         const int c_split = (((p.cout >> 4) + 1) >> 1) << 4;   // 16-column groups: first ceil(n/2) to half 0, rest to half 1
         const int c_begin = half ? c_split : 0, c_end = half ? p.cout : c_split;
+        const int et = threadIdx.x;                          // 0..255
+        const int esz = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 4;
+        const int n_planes = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 1;
+        const int cpr = (p.cout * esz) >> 4;                 // 16-B chunks per pixel row
+        const unsigned magic_cpr = (unsigned)((0x100000000ull + cpr - 1) / cpr);
+        const uint32_t epi_plane = (uint32_t)TILE_M * p.epi_pitch;
+        long long* row_base = reinterpret_cast<long long*>(epi + (size_t)n_planes * epi_plane);
+        const bool staged = p.epi_bytes > 0;
         int it = 0;
-        long long e_wait = 0, e_total0 = TCLK();
+        long long e_wait = 0, e_total0 = TCLK(), e_p1 = 0, e_bar = 0, e_p2 = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int as = it % p.acc_stages;
             const TileCoord tc = tile_coord(p, tile);
@@ -383,8 +453,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             if (p.ksize == 1) {
                 const long long gp = tc.pix0 + r;
                 valid = gp < p.total_pix;
-                oimg = valid ? (int)(gp / hw_out) : 0;
-                opin = valid ? (int)(gp - (long long)oimg * hw_out) : 0;
+                const unsigned gpu = valid ? (unsigned)gp : 0u;
+                oimg = (int)(gpu / (unsigned)hw_out);
+                opin = (int)(gpu - (unsigned)oimg * (unsigned)hw_out);
             } else {
                 const int oy = tc.oy0 + (r >> 3), ox = tc.ox0 + (r & 7);
                 valid = (oy < p.Ho && ox < p.Wo);
@@ -393,12 +464,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
             const long long obase = (long long)oimg * p.out_img + (long long)opin * p.out_C + p.out_coff;
             const long long rbase = (long long)oimg * p.res_img + (long long)opin * p.res_C + p.res_coff;
+            if (staged && half == 0) row_base[r] = valid ? obase : -1;
             { long long t0 = TCLK();
               mbar_wait(&acc_full[as], (it / p.acc_stages) & 1);
               e_wait += TCLK() - t0; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long tp1 = TCLK();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.acc_stride);
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            for (int c0 = c_begin; c0 < ((p.dbg_flags & 2) ? c_begin : c_end); c0 += 16) {
                 uint32_t v[16], v2[16];
                 tmem_ld16(trow + c0, v);                       // Ahi*Bhi + Alo*Bhi
                 tmem_ld16(trow + p.cout + c0, v2);             // Ahi*Blo
@@ -446,11 +519,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                         h2[i] = hi;
                         l2[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
                     }
-                    __half* o = reinterpret_cast<__half*>(p.out) + obase + c0;
-                    *reinterpret_cast<uint4*>(o) = oh[0];
-                    *reinterpret_cast<uint4*>(o + 8) = oh[1];
-                    *reinterpret_cast<uint4*>(o + p.out_plane) = ol[0];
-                    *reinterpret_cast<uint4*>(o + p.out_plane + 8) = ol[1];
+                    if (staged) {
+                        uint8_t* sp = epi + (size_t)r * p.epi_pitch + c0 * 2;
+                        *reinterpret_cast<uint4*>(sp) = oh[0];
+                        *reinterpret_cast<uint4*>(sp + 16) = oh[1];
+                        *reinterpret_cast<uint4*>(sp + epi_plane) = ol[0];
+                        *reinterpret_cast<uint4*>(sp + epi_plane + 16) = ol[1];
+                    } else {
+                        __half* o = reinterpret_cast<__half*>(p.out) + obase + c0;
+                        *reinterpret_cast<uint4*>(o) = oh[0];
+                        *reinterpret_cast<uint4*>(o + 8) = oh[1];
+                        *reinterpret_cast<uint4*>(o + p.out_plane) = ol[0];
+                        *reinterpret_cast<uint4*>(o + p.out_plane + 8) = ol[1];
+                    }
+                } else if (staged) {
+                    uint8_t* sp = epi + (size_t)r * p.epi_pitch + c0 * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<float4*>(sp + 16 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
                 } else {
                     float* o = reinterpret_cast<float*>(p.out) + obase + c0;
 #pragma unroll
@@ -459,9 +545,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[as]);
+            mbar_arrive(&acc_empty[as]);                     // accumulator drained: the MMA warp may reuse it
+            const long long tp2 = TCLK();
+            e_p1 += tp2 - tp1;
+            if (staged && !(p.dbg_flags & 2)) {
+                asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tile complete (epilogue warps only)
+                const long long tp3 = TCLK();
+                e_bar += tp3 - tp2;
+                const int per_plane = TILE_M * cpr;
+                for (int q = et; q < n_planes * per_plane; q += 256) {
+                    const int pl = q >= per_plane ? 1 : 0;
+                    const int qq = q - pl * per_plane;
+                    const int row = (int)__umulhi((unsigned)qq, magic_cpr);
+                    const int ch = qq - row * cpr;
+                    const long long base = row_base[row];
+                    if (base < 0) continue;
+                    const uint4 val = *reinterpret_cast<const uint4*>(epi + (size_t)pl * epi_plane + (size_t)row * p.epi_pitch + ch * 16);
+                    uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + ((base + (long long)pl * p.out_plane) * esz) + ch * 16;
+                    *reinterpret_cast<uint4*>(o) = val;
+                }
+                const long long tp4 = TCLK();
+                asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tile free for the next tile
+                e_p2 += tp4 - tp3;
+                e_bar += TCLK() - tp4;
+            }
         }
-        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[12] = e_p2; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -499,6 +608,7 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
         p.res_img = rb.image_bytes / 2; p.res_plane = (long long)net.max_batch * p.res_img; p.res_C = rb.c; p.res_coff = op.res_coff;
     }
     p.dbg = ctx->tc_dbg;
+    { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_DEBUG"); f = e ? atoi(e) : 0; } p.dbg_flags = f; }
     p.wtc = net.weights_tc + op.wtc_off;
     p.bias = net.weights + op.b_off;
     p.cin = op.cin; p.cout = op.cout; p.act = op.act;
@@ -521,31 +631,45 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
     const size_t patch_bytes = (size_t)2 * (op.cin / 8) * p.slots_p * 16;
     p.tab_bytes = op.ksize == 3 ? ((op.cin / 8) * p.slots * 4 + 127) / 128 * 128 : 0;
     if (op.ksize == 1 && ib.image_bytes != (int64_t)ib.h * ib.w * ib.c * 2) return 0;
-    const size_t budget = 220 * 1024 - 512 - p.tab_bytes;
+    p.n_mma = p.n_kb * (p.kb_ch / 16) * 2;
+    p.mtab_bytes = (p.n_mma * 8 + 127) / 128 * 128;
+    const int out_row_bytes = op.cout * (ob.fmt == LP_FMT_SPLIT16 ? 2 : 4);
+    p.epi_pitch = out_row_bytes + 16;
+    const size_t epi_full = (size_t)(ob.fmt == LP_FMT_SPLIT16 ? 2 : 1) * TILE_M * p.epi_pitch + TILE_M * 8;
+    const size_t total = 220 * 1024 - 512 - p.tab_bytes - p.mtab_bytes;
     const size_t w_all = (size_t)p.n_kb * p.stage_bytes;
-    // weights resident if the whole layer fits beside >= 2 patch stages, else a streaming ring; the rest of
-    // shared memory goes to patch stages (deep prefetch: the small-channel layers are latency/HBM-bound)
-    p.patch_stages = 0;
-    if (w_all + 2 * patch_bytes <= budget && p.n_kb <= MAX_WST) { p.resident = 1; p.w_stages = p.n_kb; }
-    else {
-        p.resident = 0;
-        const int min_ps = (2 * patch_bytes + 2 * (size_t)p.stage_bytes <= budget) ? 2 : 1;
-        if (min_ps * patch_bytes + 2 * (size_t)p.stage_bytes > budget) return 0;
-        int s = (int)((budget - min_ps * patch_bytes) / p.stage_bytes);
-        p.w_stages = s > 4 ? 4 : s;
-        if (p.w_stages > p.n_kb) p.w_stages = p.n_kb;
-    }
-    {
+    // Shared-memory plan.  Weights: resident if the whole layer fits beside >= 2 patch stages, else a ring
+    // whose stage count divides n_kb (so the stage pattern is identical for every tile).  Epilogue staging
+    // (coalesced stores) if >= 2 patch stages still fit.  Everything left goes to patch stages.
+    auto plan = [&](bool stage_epi) -> bool {
+        const size_t budget = total - (stage_epi ? epi_full : 0);
+        if (total < (stage_epi ? epi_full : 0)) return false;
+        if (w_all + 2 * patch_bytes <= budget && p.n_kb <= MAX_WST) { p.resident = 1; p.w_stages = p.n_kb; }
+        else {
+            p.resident = 0;
+            const int min_ps = (2 * patch_bytes + 2 * (size_t)p.stage_bytes <= budget) ? 2 : 1;
+            if (min_ps * patch_bytes + 2 * (size_t)p.stage_bytes > budget) return false;
+            int cap = (int)((budget - min_ps * patch_bytes) / p.stage_bytes);
+            if (cap > 4) cap = 4;
+            int ws = 0;
+            for (int d = cap; d >= 2; --d) if (p.n_kb % d == 0) { ws = d; break; }
+            if (!ws) return false;
+            p.w_stages = ws;
+        }
         const size_t left = budget - (size_t)p.w_stages * p.stage_bytes;
         int ps = (int)(left / patch_bytes);
         p.patch_stages = ps > MAX_PST ? MAX_PST : ps;
-        if (p.patch_stages < 1) return 0;
-    }
+        if (p.patch_stages < 1) return false;
+        p.epi_bytes = stage_epi ? (int)epi_full : 0;
+        return !stage_epi || p.patch_stages >= 2;
+    };
+    if (!plan(true) && !plan(false)) return 0;
+    p.fills_per_tile = p.resident ? 0 : p.n_kb / p.w_stages;
     p.acc_stride = 2 * op.cout < 32 ? 32 : 2 * op.cout;        // [Ahi*Bhi+Alo*Bhi | Ahi*Blo]
     p.acc_stages = 512 / p.acc_stride > MAX_AST ? MAX_AST : 512 / p.acc_stride;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_stages * p.acc_stride) p.tmem_cols <<= 1;
-    const size_t smem = 512 + (size_t)p.patch_stages * patch_bytes + (size_t)p.w_stages * p.stage_bytes + p.tab_bytes;
+    const size_t smem = 512 + (size_t)p.patch_stages * patch_bytes + (size_t)p.w_stages * p.stage_bytes + p.tab_bytes + p.mtab_bytes + p.epi_bytes;
 
     if (op.ksize == 1) {
         p.total_pix = (long long)batch * ib.h * ib.w;
