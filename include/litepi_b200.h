@@ -37,7 +37,7 @@ extern "C" {
 
 typedef struct lp_ctx lp_ctx;
 
-#define LP_ABI_VERSION 1
+#define LP_ABI_VERSION 2
 
 /* ---- network plan (built on the host from the reference's model.ncnn.param) ---- */
 
@@ -71,6 +71,11 @@ typedef struct lp_op_desc {
     int32_t in_buf, in_coff, cin;
     int32_t out_buf, out_coff, cout;
     int32_t out_cstride;                /* 1, or 2 for shuffle-interleaved stores */
+    int32_t cout_real;                  /* outputs actually stored (<= cout; the rest is tensor-core N padding) */
+    int32_t out_seg_len, out_seg_pad;   /* > 0: segmented destination.  Output j is LOGICAL channel
+                                           l = out_coff + j*out_cstride and lands on physical channel
+                                           (l / out_seg_len) * out_seg_pad + l % out_seg_len (ShuffleNetV2 halves
+                                           of 58/116/232 channels padded to 64/128/256) */
     int32_t res_buf, res_coff;          /* residual added AFTER the activation (-1 = none) */
     int32_t ksize, stride, act;
     int32_t row_off;                    /* Detect head: first anchor row this level writes */

@@ -59,6 +59,11 @@ def run_plan_cpu(plan, x_u8: np.ndarray):
         if plan.bufs[op["out_buf"]]["w"] == 1 and plan.bufs[op["out_buf"]]["h"] > 1:      # Detect head rows
             rows = y.shape[1] * y.shape[2]
             ob[:, op["row_off"]:op["row_off"] + rows, 0, op["out_coff"]:op["out_coff"] + cout] = y.reshape(B, rows, cout)
+        elif op.get("out_seg_len", 0) > 0:                                 # segmented (shuffled) destination
+            n = op["cout_real"]
+            l = op["out_coff"] + cs * np.arange(n)
+            phys = (l // op["out_seg_len"]) * op["out_seg_pad"] + l % op["out_seg_len"]
+            ob[..., torch.from_numpy(phys)] = y[..., :n]
         else:
             ob[..., op["out_coff"]:op["out_coff"] + cs * cout:cs] = y
     return bufs, logits

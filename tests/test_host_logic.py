@@ -98,7 +98,7 @@ def test_abi_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(L.BufDesc) == 32
-    assert ctypes.sizeof(L.OpDesc) == 14 * 4 + 2 * 4 + 3 * 8
+    assert ctypes.sizeof(L.OpDesc) == 17 * 4 + 2 * 4 + 4 + 3 * 8      # 17 int32, 2 float, pad, 3 int64
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

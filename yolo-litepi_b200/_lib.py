@@ -16,7 +16,7 @@ OP_STEM_U8, OP_CONV, OP_DWCONV3, OP_MAXPOOL, OP_UPSAMPLE2, OP_COPY, OP_MEAN_FC =
 ACT_NONE, ACT_SILU, ACT_RELU = range(3)
 FMT_SPLIT16, FMT_F32, FMT_U8 = range(3)
 NET_DETECTOR, NET_CLASSIFIER = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class BufDesc(C.Structure):
@@ -27,7 +27,8 @@ class BufDesc(C.Structure):
 class OpDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("in_buf", C.c_int32), ("in_coff", C.c_int32), ("cin", C.c_int32),
                 ("out_buf", C.c_int32), ("out_coff", C.c_int32), ("cout", C.c_int32),
-                ("out_cstride", C.c_int32), ("res_buf", C.c_int32), ("res_coff", C.c_int32),
+                ("out_cstride", C.c_int32), ("cout_real", C.c_int32), ("out_seg_len", C.c_int32),
+                ("out_seg_pad", C.c_int32), ("res_buf", C.c_int32), ("res_coff", C.c_int32),
                 ("ksize", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32),
                 ("row_off", C.c_int32), ("in_mean", C.c_float), ("in_std", C.c_float),
                 ("w_off", C.c_int64), ("b_off", C.c_int64), ("wtc_off", C.c_int64)]

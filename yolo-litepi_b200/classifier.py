@@ -30,7 +30,8 @@ def _random_state_dict(num_classes: int, seed: Optional[int]):
 class B200Classifier:
     def __init__(self, model_path: Optional[str], arch: str = "shufflenetv2", num_classes: int = 58,
                  input_size: int = 64, device="cpu", state_dict: Optional[dict] = None,
-                 cuda_device: int = 0, max_batch: int = 256, seed: Optional[int] = None):
+                 cuda_device: int = 0, max_batch: int = 256, seed: Optional[int] = None,
+                 tensor_cores: bool = True):
         # `device` is the reference's torch device string (e2e.py:354); this backend always runs on
         # cuda:`cuda_device`.  Only shufflenetv2 is implemented (ValueError like e2e.py:335 otherwise).
         if arch != "shufflenetv2":
@@ -59,12 +60,17 @@ class B200Classifier:
             raise ValueError("state_dict fc size does not match num_classes")
         self.max_batch = int(max_batch)
         ws_bytes = self.plan.layout(self.max_batch)
+        tc_blob = self.plan.pack_tc_weights() if tensor_cores else np.zeros(0, np.uint8)
+        self.tc_ops = sum(1 for o in self.plan.ops if o["wtc_off"] >= 0)
         with torch.cuda.device(self.device):
             self.weights = torch.from_numpy(self.plan.weights()).to(self.device)
+            self.weights_tc = torch.from_numpy(tc_blob).to(self.device) if tc_blob.size else None
+            # zero-initialised: the padding channels of the shuffled halves are never written
             self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
             bufs, ops = self.plan.c_arrays()
             L.check(L.lib().lp_net_load(self.ctx.handle, L.NET_CLASSIFIER, bufs, len(bufs), ops, len(ops),
-                                        _ptr(self.weights), self.weights.numel(), None, 0, self.max_batch),
+                                        _ptr(self.weights), self.weights.numel(), _ptr(self.weights_tc),
+                                        tc_blob.size, self.max_batch),
                     "lp_net_load(classifier)")
         self._cap = 0
         self._alloc(self.max_batch)

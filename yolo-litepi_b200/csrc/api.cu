@@ -116,7 +116,14 @@ extern "C" int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int 
         LP_CHECK(o.in_coff >= 0 && o.in_coff + o.cin <= P.bufs[o.in_buf].c, "lp_net_load: op %d input slice exceeds buffer", i);
         if (o.kind != LP_OP_MEAN_FC) {
             const int cs = o.out_cstride > 0 ? o.out_cstride : 1;
-            LP_CHECK(o.out_coff >= 0 && o.out_coff + (o.cout - 1) * cs < P.bufs[o.out_buf].c, "lp_net_load: op %d output slice exceeds buffer", i);
+            const int n_out = o.cout_real > 0 ? o.cout_real : o.cout;
+            if (o.out_seg_len > 0) {
+                const int l = o.out_coff + (n_out - 1) * cs;
+                LP_CHECK(o.out_seg_pad >= o.out_seg_len && (l / o.out_seg_len) * o.out_seg_pad + l % o.out_seg_len < P.bufs[o.out_buf].c,
+                         "lp_net_load: op %d segmented output exceeds buffer", i);
+            } else {
+                LP_CHECK(o.out_coff >= 0 && o.out_coff + (n_out - 1) * cs < P.bufs[o.out_buf].c, "lp_net_load: op %d output slice exceeds buffer", i);
+            }
         }
         const size_t wn = o.kind == LP_OP_CONV || o.kind == LP_OP_STEM_U8 ? (size_t)o.ksize * o.ksize * o.cin * o.cout
                           : o.kind == LP_OP_DWCONV3 ? (size_t)9 * o.cout

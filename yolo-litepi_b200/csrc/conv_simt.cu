@@ -19,6 +19,7 @@ struct TensorRef {
 struct ConvParams {
     TensorRef in, out, res;  // res.base == nullptr -> no residual
     int cin, cout, out_cstride;
+    int cout_real, seg_l0, seg_len, seg_pad;   // segmented destination (lp_op_desc.out_seg_len); seg_len == 0: plain
     int H, W, Ho, Wo;        // input / output spatial size
     int ksize, stride, act;
     int n_img;
@@ -31,6 +32,15 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == LP_ACT_SILU) return v / (1.f + __expf(-v));
     if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
     return v;
+}
+
+// physical channel (relative to the pixel) of output j
+__device__ __forceinline__ long long out_chan(const ConvParams& p, int j) {
+    if (p.seg_len > 0) {
+        const int l = p.seg_l0 + j * p.out_cstride;
+        return (long long)(l / p.seg_len) * p.seg_pad + l % p.seg_len;
+    }
+    return (long long)j * p.out_cstride;
 }
 
 __device__ __forceinline__ float ld_elem(const TensorRef& t, long long idx) {
@@ -230,8 +240,8 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(ConvParams p) {
             if (p.res.base && i < n) x += r[i];
             v[i] = x;
         }
-        if (n == 8 && p.out_cstride == 1 && (p.out.fmt == LP_FMT_SPLIT16)) st8(p.out, opix + cbase, v);
-        else for (int i = 0; i < n; ++i) st_elem(p.out, opix + (long long)(cbase + i) * p.out_cstride, v[i]);
+        if (n == 8 && p.out_cstride == 1 && p.seg_len == 0 && (p.out.fmt == LP_FMT_SPLIT16)) st8(p.out, opix + cbase, v);
+        else for (int i = 0; i < n; ++i) if (cbase + i < p.cout_real) st_elem(p.out, opix + out_chan(p, cbase + i), v[i]);
     }
 }
 
@@ -329,7 +339,7 @@ __global__ void dwconv3_kernel(ConvParams p) {
         }
     }
     acc = act_apply(acc, p.act);
-    st_elem(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + (long long)c * p.out_cstride, acc);
+    st_elem(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + out_chan(p, c), acc);
 }
 
 __global__ void maxpool_kernel(ConvParams p) {
@@ -367,7 +377,7 @@ __global__ void resample_copy_kernel(ConvParams p) {
     const int img = (int)(r / p.Ho);
     const int iy = oy / p.stride, ix = ox / p.stride;
     const long long src = (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff + c;
-    const long long dst = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + (long long)c * p.out_cstride;
+    const long long dst = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + out_chan(p, c);
     if (p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16) {   // bit-preserving
         const __half* s = (const __half*)p.in.base;
         __half* d = (__half*)p.out.base;
@@ -376,6 +386,57 @@ __global__ void resample_copy_kernel(ConvParams p) {
     } else {
         st_elem(p.out, dst, ld_elem(p.in, src));
     }
+}
+
+// Vectorised split-f16 variants: one thread = one 16-byte chunk (8 channels) of one plane of one output
+// pixel; both the nearest-x2 upsample (stride 2) and the copy (stride 1) are bit-preserving.
+__global__ void resample_copy8_kernel(ConvParams p) {
+    const int cpp = p.cout >> 3;                                      // chunks per pixel
+    const long long total = 2LL * p.n_img * p.Ho * p.Wo * cpp;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ch = (int)(i % cpp);
+    long long r = i / cpp;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho); r /= p.Ho;
+    const int img = (int)(r % p.n_img);
+    const int plane = (int)(r / p.n_img);
+    const int iy = oy / p.stride, ix = ox / p.stride;
+    const __half* s = (const __half*)p.in.base + (long long)plane * p.in.plane + (long long)img * p.in.img +
+                      ((long long)iy * p.W + ix) * p.in.C + p.in.coff + ch * 8;
+    __half* d = (__half*)p.out.base + (long long)plane * p.out.plane + (long long)img * p.out.img +
+                ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + ch * 8;
+    *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(s));
+}
+
+// max pool on split-f16, 8 channels per thread.  max(hi+lo) is taken on the reconstructed fp32 values.
+__global__ void maxpool8_kernel(ConvParams p) {
+    const int cpp = p.cout >> 3;
+    const long long total = (long long)p.n_img * p.Ho * p.Wo * cpp;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ch = (int)(i % cpp);
+    long long r = i / cpp;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int img = (int)(r / p.Ho);
+    const int pad = p.ksize / 2;
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+    for (int ky = 0; ky < p.ksize; ++ky) {
+        const int iy = oy * p.stride - pad + ky;
+        if (iy < 0 || iy >= p.H) continue;
+        for (int kx = 0; kx < p.ksize; ++kx) {
+            const int ix = ox * p.stride - pad + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            float v[8];
+            ld8(p.in, (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff + ch * 8, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+        }
+    }
+    st8(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + ch * 8, m);
 }
 
 // global mean over HxW then FC: logits[img][j] = bias[j] + sum_c mean_c * w[c][j]   (w stored [cin][cout])
@@ -447,6 +508,8 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
         ConvParams p{};
         const lp_buf_desc& ob = net.bufs[op.out_buf >= 0 ? op.out_buf : op.in_buf];
         p.cin = op.cin; p.cout = op.cout; p.out_cstride = op.out_cstride > 0 ? op.out_cstride : 1;
+        p.cout_real = op.cout_real > 0 ? op.cout_real : op.cout;
+        p.seg_len = op.out_seg_len; p.seg_pad = op.out_seg_pad; p.seg_l0 = op.out_seg_len > 0 ? op.out_coff : 0;
         p.ksize = op.ksize; p.stride = op.stride; p.act = op.act; p.n_img = batch;
         p.w = net.weights + op.w_off; p.bias = net.weights + op.b_off;
         p.in_scale_mean = 0.f; p.in_scale_std = 1.f;
@@ -463,7 +526,7 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             if (op.kind == LP_OP_CONV) p.res = make_ref(net, op.res_buf, op.res_coff, ws, 0);
         }
         if (op.kind != LP_OP_MEAN_FC) {
-            p.out = make_ref(net, op.out_buf, op.out_coff, ws, op.row_off);
+            p.out = make_ref(net, op.out_buf, op.out_seg_len > 0 ? 0 : op.out_coff, ws, op.row_off);
             p.Ho = (op.kind == LP_OP_UPSAMPLE2) ? p.H * 2 : (op.kind == LP_OP_COPY ? p.H : (p.H + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
             p.Wo = (op.kind == LP_OP_UPSAMPLE2) ? p.W * 2 : (op.kind == LP_OP_COPY ? p.W : (p.W + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
             if (!(ob.w == 1 && ob.h > 1))     // Detect-head row buffers ([anchors][C]) are addressed through row_off
@@ -495,17 +558,22 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
         case LP_OP_DWCONV3:
             dwconv3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
             break;
-        case LP_OP_MAXPOOL:
-            maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+        case LP_OP_MAXPOOL: {
+            const bool v8 = p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16 && p.cout % 8 == 0 &&
+                            p.in.coff % 8 == 0 && p.out.coff % 8 == 0 && p.out_cstride == 1 && p.seg_len == 0;
+            if (v8) maxpool8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, st>>>(p);
+            else maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
             break;
+        }
         case LP_OP_UPSAMPLE2:
-            p.stride = 2;
-            resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+        case LP_OP_COPY: {
+            p.stride = op.kind == LP_OP_UPSAMPLE2 ? 2 : 1;
+            const bool v8 = p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16 && p.cout % 8 == 0 &&
+                            p.in.coff % 8 == 0 && p.out.coff % 8 == 0 && p.out_cstride == 1 && p.seg_len == 0;
+            if (v8) resample_copy8_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(p);
+            else resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
             break;
-        case LP_OP_COPY:
-            p.stride = 1;
-            resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
-            break;
+        }
         case LP_OP_MEAN_FC:
             LP_CHECK(logits != nullptr, "mean_fc: logits pointer is null");
             mean_fc_kernel<<<batch, 256, op.cin * sizeof(float), st>>>(p, logits);

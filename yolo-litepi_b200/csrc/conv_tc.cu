@@ -49,6 +49,7 @@ struct TcParams {
     const uint8_t* wtc;        // packed split weights of this op
     const float* bias;
     int cin, cout, act;
+    int cout_real, out_cstride, seg_l0, seg_len, seg_pad;   // segmented (channel-shuffle) destination; seg_len == 0: plain
     int H, W, Ho, Wo;          // input / output spatial size
     int n_img, tiles_x, tiles_y, n_tiles;
     int ksize, stride;
@@ -519,7 +520,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                         h2[i] = hi;
                         l2[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
                     }
-                    if (staged) {
+                    if (p.seg_len > 0) {                   // element scatter (ShuffleNetV2 channel shuffle)
+                        __half* o = reinterpret_cast<__half*>(p.out) + (long long)oimg * p.out_img + (long long)opin * p.out_C;
+                        const __half* hh = reinterpret_cast<const __half*>(oh);
+                        const __half* ll = reinterpret_cast<const __half*>(ol);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int j = c0 + i;
+                            if (j < p.cout_real) {
+                                const int l = p.seg_l0 + j * p.out_cstride;
+                                const int ph = (l / p.seg_len) * p.seg_pad + l % p.seg_len;
+                                o[ph] = hh[i];
+                                o[ph + p.out_plane] = ll[i];
+                            }
+                        }
+                    } else if (staged) {
                         uint8_t* sp = epi + (size_t)r * p.epi_pitch + c0 * 2;
                         *reinterpret_cast<uint4*>(sp) = oh[0];
                         *reinterpret_cast<uint4*>(sp + 16) = oh[1];
@@ -583,15 +598,44 @@ unsigned magic_u32(int n) { return (unsigned)((0x100000000ull + (unsigned)n - 1)
 
 }  // namespace
 
+static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st,
+                         int n0, int nb, size_t wtc_off);
+
 // returns 1 if the op ran on the tensor cores, 0 if it is not eligible, <0 on error
 int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st) {
+    const lp_buf_desc& ib = net.bufs[op.in_buf];
+    if (op.kind != LP_OP_CONV || ib.fmt != LP_FMT_SPLIT16 || op.cout % 16) return 0;
+    int kb_ch = 0;
+    for (int d : {64, 48, 32, 16}) if (op.cin % d == 0) { kb_ch = d; break; }
+    if (!kb_ch) return 0;
+    // output channels in blocks of <= 128 (N of the [Bhi|Blo] MMA is 2*block <= 256); the packed weights
+    // hold the blocks back to back (plan.py pack_tc_weights)
+    size_t woff = 0;
+    for (int n0 = 0; n0 < op.cout; n0 += 128) {
+        const int nb = op.cout - n0 < 128 ? op.cout - n0 : 128;
+        const int r = conv_tc_block(ctx, net, op, batch, ws, st, n0, nb, woff);
+        if (r != 1) {
+            if (n0 == 0) return r;
+            lp_set_error("conv_tc: output block %d of an op became ineligible", n0);
+            return -1;
+        }
+        woff += (size_t)op.ksize * op.ksize * op.cin * nb * 4;
+        if (n0 + 128 < op.cout) ctx->launches++;
+    }
+    return 1;
+}
+
+static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st,
+                         int n0, int nb, size_t wtc_off) {
     const lp_buf_desc& ib = net.bufs[op.in_buf];
     const lp_buf_desc& ob = net.bufs[op.out_buf];
     if (op.kind != LP_OP_CONV || ib.fmt != LP_FMT_SPLIT16) return 0;
     if (!((op.ksize == 1 && op.stride == 1) || (op.ksize == 3 && (op.stride == 1 || op.stride == 2)))) return 0;
-    if (op.cin % 16 || op.cout % 16 || op.cout > 128 || op.cin > 512 || op.in_coff % 8 || op.out_coff % 4) return 0;
-    if (op.out_cstride > 1) return 0;
-    if (ob.fmt == LP_FMT_SPLIT16 && op.out_coff % 8) return 0;
+    const bool seg = op.out_seg_len > 0;
+    if (op.cin % 16 || nb % 16 || op.cin > 512 || op.in_coff % 8) return 0;
+    if (!seg && (op.out_cstride > 1 || op.out_coff % 4)) return 0;
+    if (seg && ob.fmt != LP_FMT_SPLIT16) return 0;
+    if (!seg && ob.fmt == LP_FMT_SPLIT16 && op.out_coff % 8) return 0;
 
     TcParams p{};
     const long long in_img = ib.image_bytes / 2;
@@ -600,7 +644,7 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
     const int oesz = ob.fmt == LP_FMT_SPLIT16 ? 2 : 4;
     p.out = ws + ob.offset + (size_t)op.row_off * ob.c * oesz;
     p.out_img = ob.image_bytes / oesz; p.out_plane = (long long)net.max_batch * p.out_img;
-    p.out_C = ob.c; p.out_coff = op.out_coff; p.out_fmt = ob.fmt;
+    p.out_C = ob.c; p.out_coff = seg ? 0 : op.out_coff; p.out_fmt = ob.fmt;
     if (op.res_buf >= 0) {
         const lp_buf_desc& rb = net.bufs[op.res_buf];
         if (rb.fmt != LP_FMT_SPLIT16 || op.res_coff % 8) return 0;
@@ -609,9 +653,15 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
     }
     p.dbg = ctx->tc_dbg;
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_DEBUG"); f = e ? atoi(e) : 0; } p.dbg_flags = f; }
-    p.wtc = net.weights_tc + op.wtc_off;
-    p.bias = net.weights + op.b_off;
-    p.cin = op.cin; p.cout = op.cout; p.act = op.act;
+    p.wtc = net.weights_tc + op.wtc_off + wtc_off;
+    p.bias = net.weights + op.b_off + n0;
+    p.cin = op.cin; p.cout = nb; p.act = op.act;
+    p.out_cstride = op.out_cstride > 0 ? op.out_cstride : 1;
+    p.seg_len = op.out_seg_len; p.seg_pad = op.out_seg_pad;
+    p.seg_l0 = seg ? op.out_coff + n0 * p.out_cstride : 0;
+    const int real_all = op.cout_real > 0 ? op.cout_real : n0 + nb;
+    p.cout_real = real_all - n0 < nb ? (real_all - n0 < 0 ? 0 : real_all - n0) : nb;
+    if (!seg) p.out_coff += n0;
     p.H = ib.h; p.W = ib.w; p.n_img = batch; p.ksize = op.ksize; p.stride = op.stride;
     p.Ho = (ib.h + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1;
     p.Wo = (ib.w + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1;
@@ -633,7 +683,7 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
     if (op.ksize == 1 && ib.image_bytes != (int64_t)ib.h * ib.w * ib.c * 2) return 0;
     p.n_mma = p.n_kb * (p.kb_ch / 16) * 2;
     p.mtab_bytes = (p.n_mma * 8 + 127) / 128 * 128;
-    const int out_row_bytes = op.cout * (ob.fmt == LP_FMT_SPLIT16 ? 2 : 4);
+    const int out_row_bytes = nb * (ob.fmt == LP_FMT_SPLIT16 ? 2 : 4);
     p.epi_pitch = out_row_bytes + 16;
     const size_t epi_full = (size_t)(ob.fmt == LP_FMT_SPLIT16 ? 2 : 1) * TILE_M * p.epi_pitch + TILE_M * 8;
     const size_t total = 220 * 1024 - 512 - p.tab_bytes - p.mtab_bytes;
@@ -663,9 +713,9 @@ int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batc
         p.epi_bytes = stage_epi ? (int)epi_full : 0;
         return !stage_epi || p.patch_stages >= 2;
     };
-    if (!plan(true) && !plan(false)) return 0;
+    if (!((!seg && plan(true)) || plan(false))) return 0;
     p.fills_per_tile = p.resident ? 0 : p.n_kb / p.w_stages;
-    p.acc_stride = 2 * op.cout < 32 ? 32 : 2 * op.cout;        // [Ahi*Bhi+Alo*Bhi | Ahi*Blo]
+    p.acc_stride = 2 * nb < 32 ? 32 : 2 * nb;        // [Ahi*Bhi+Alo*Bhi | Ahi*Blo]
     p.acc_stages = 512 / p.acc_stride > MAX_AST ? MAX_AST : 512 / p.acc_stride;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_stages * p.acc_stride) p.tmem_cols <<= 1;

@@ -28,6 +28,10 @@ def p8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
+def pad_to(c: int, g: int) -> int:
+    return (c + g - 1) // g * g
+
+
 @dataclass
 class View:
     """A run of logical channel segments inside one buffer; segment i holds ``lens[i]``
@@ -36,6 +40,7 @@ class View:
     offs: Tuple[int, ...]
     lens: Tuple[int, ...]
     pad8: bool = True
+    gran: int = 8                       # padding granularity of a segment when pad8 (8 detector, 16 classifier)
 
     @property
     def start(self) -> int:
@@ -44,7 +49,7 @@ class View:
     @property
     def phys(self) -> int:
         last = self.lens[-1]
-        return self.offs[-1] + (p8(last) if self.pad8 else last) - self.offs[0]
+        return self.offs[-1] + (pad_to(last, self.gran) if self.pad8 else last) - self.offs[0]
 
     @property
     def logical(self) -> int:
@@ -59,7 +64,7 @@ class View:
 
     def seg(self, i: int, j: Optional[int] = None) -> "View":
         j = i + 1 if j is None else j
-        return View(self.buf, self.offs[i:j], self.lens[i:j], self.pad8)
+        return View(self.buf, self.offs[i:j], self.lens[i:j], self.pad8, self.gran)
 
 
 @dataclass
@@ -77,13 +82,13 @@ class Plan:
         self.bufs.append(dict(h=h, w=w, c=c, fmt=fmt))
         return len(self.bufs) - 1
 
-    def new_view(self, h: int, w: int, lens: Sequence[int], fmt: int = L.FMT_SPLIT16) -> View:
+    def new_view(self, h: int, w: int, lens: Sequence[int], fmt: int = L.FMT_SPLIT16, gran: int = 8) -> View:
         pad8 = fmt == L.FMT_SPLIT16
         offs, o = [], 0
         for n in lens:
             offs.append(o)
-            o += p8(n) if pad8 else n
-        return View(self.buf(h, w, o, fmt), tuple(offs), tuple(lens), pad8)
+            o += pad_to(n, gran) if pad8 else n
+        return View(self.buf(h, w, o, fmt), tuple(offs), tuple(lens), pad8, gran)
 
     # ---- weights
     def _push(self, a: np.ndarray) -> int:
@@ -103,17 +108,22 @@ class Plan:
     # ---- ops
     def conv(self, name: str, w: np.ndarray, b: Optional[np.ndarray], src: View, dst: View, stride: int, act: int,
              res: Optional[View] = None, row_off: int = 0, out_cstride: int = 1, kind: int = L.OP_CONV,
-             in_mean: float = 0.0, in_std: float = 1.0) -> None:
-        """w: [cout, cin, k, k] (logical channels) -> packed [tap][cin_phys][cout_phys], zero padded."""
+             in_mean: float = 0.0, in_std: float = 1.0, seg: Optional[Tuple[int, int, int]] = None) -> None:
+        """w: [cout, cin, k, k] (logical channels) -> packed [tap][cin_phys][cout_phys], zero padded.
+        ``seg`` = (logical offset, segment length, padded segment length): output j goes to LOGICAL channel
+        off + j*out_cstride of a buffer whose logical channels are stored in padded segments."""
         cout, cin, k, _ = w.shape
         assert cin == src.logical, f"{name}: cin {cin} != view {src.logical}"
-        assert cout == dst.logical, f"{name}: cout {cout} != view {dst.logical}"
+        assert seg is not None or cout == dst.logical, f"{name}: cout {cout} != view {dst.logical}"
         hi, wi = self.bufs[src.buf]["h"], self.bufs[src.buf]["w"]
         cinp = src.phys if kind != L.OP_STEM_U8 else 3
-        coutp = dst.phys if out_cstride == 1 else cout
+        if seg is not None:
+            coutp = pad_to(cout, 16)                   # N padding for the tensor core; only `cout` are stored
+        else:
+            coutp = dst.phys if out_cstride == 1 else cout
         wp = np.zeros((k * k, cinp, coutp), np.float32)
         im = src.chan_map() if kind != L.OP_STEM_U8 else np.arange(3)
-        om = dst.chan_map() if out_cstride == 1 else np.arange(cout)
+        om = dst.chan_map() if (out_cstride == 1 and seg is None) else np.arange(cout)
         wp[:, im[:, None], om[None, :]] = w.transpose(2, 3, 1, 0).reshape(k * k, cin, cout)
         bp = np.zeros(coutp, np.float32)
         if b is not None:
@@ -123,7 +133,9 @@ class Plan:
         ho = (hi + 2 * (k // 2) - k) // stride + 1
         wo = (wi + 2 * (k // 2) - k) // stride + 1
         self.ops.append(dict(kind=kind, in_buf=src.buf, in_coff=src.start if kind != L.OP_STEM_U8 else 0, cin=cinp,
-                             out_buf=dst.buf, out_coff=dst.start, cout=coutp, out_cstride=out_cstride,
+                             out_buf=dst.buf, out_coff=seg[0] if seg else dst.start, cout=coutp, out_cstride=out_cstride,
+                             cout_real=cout if seg else coutp, out_seg_len=seg[1] if seg else 0,
+                             out_seg_pad=seg[2] if seg else 0,
                              res_buf=res.buf if res is not None else -1, res_coff=res.start if res is not None else 0,
                              ksize=k, stride=stride, act=act, row_off=row_off, in_mean=in_mean, in_std=in_std,
                              w_off=self._push(wp), b_off=self._push(bp), wtc_off=-1))
@@ -132,12 +144,14 @@ class Plan:
 
     def simple(self, kind: int, name: str, src: View, dst: View, ksize: int = 1, stride: int = 1,
                out_cstride: int = 1, w: Optional[np.ndarray] = None, b: Optional[np.ndarray] = None,
-               act: int = L.ACT_NONE) -> None:
-        n = src.phys if out_cstride == 1 else src.logical
+               act: int = L.ACT_NONE, seg: Optional[Tuple[int, int, int]] = None) -> None:
+        n = src.phys if (out_cstride == 1 and seg is None) else src.logical
         w_off = self._push(w) if w is not None else 0
         b_off = self._push(b) if b is not None else 0
-        self.ops.append(dict(kind=kind, in_buf=src.buf, in_coff=src.start, cin=n, out_buf=dst.buf, out_coff=dst.start,
-                             cout=n, out_cstride=out_cstride, res_buf=-1, res_coff=0, ksize=ksize, stride=stride,
+        self.ops.append(dict(kind=kind, in_buf=src.buf, in_coff=src.start, cin=n, out_buf=dst.buf,
+                             out_coff=seg[0] if seg else dst.start,
+                             cout=n, out_cstride=out_cstride, cout_real=n, out_seg_len=seg[1] if seg else 0,
+                             out_seg_pad=seg[2] if seg else 0, res_buf=-1, res_coff=0, ksize=ksize, stride=stride,
                              act=act, row_off=0, in_mean=0.0, in_std=1.0, w_off=w_off, b_off=b_off, wtc_off=-1))
         self.names.append(name)
         self.macs.append(0)
@@ -168,12 +182,15 @@ class Plan:
         parts, off = [], 0
         for op in self.ops:
             op["wtc_off"] = -1
-            if op["kind"] != L.OP_CONV or op["out_cstride"] != 1:
+            if op["kind"] != L.OP_CONV:
                 continue
-            if (op["ksize"], op["stride"]) not in ((1, 1), (3, 1), (3, 2)):
+            seg = op["out_seg_len"] > 0
+            if (op["ksize"], op["stride"]) not in ((1, 1), (3, 1), (3, 2)) or (op["out_cstride"] != 1 and not seg):
                 continue
             cin, cout = op["cin"], op["cout"]
-            if self.bufs[op["in_buf"]]["fmt"] != L.FMT_SPLIT16 or cin % 16 or cout % 16 or cout > 128 or cin > 512:
+            if self.bufs[op["in_buf"]]["fmt"] != L.FMT_SPLIT16 or cin % 16 or cout % 16 or cin > 512:
+                continue
+            if seg and self.bufs[op["out_buf"]]["fmt"] != L.FMT_SPLIT16:
                 continue
             kb = next((d for d in (64, 48, 32, 16) if cin % d == 0), 0)      # channels per K-block
             if not kb:
@@ -182,12 +199,13 @@ class Plan:
             w = W[op["w_off"]:op["w_off"] + taps * cin * cout].reshape(taps, cin, cout)
             hi = w.astype(np.float16)
             lo = (w - hi.astype(np.float32)).astype(np.float16)
-            planes = [a.reshape(taps, ncb, kb // 8, 8, cout).transpose(0, 1, 2, 4, 3) for a in (hi, lo)]
-            blob = np.ascontiguousarray(np.stack(planes, axis=3))        # [tap][cb][chunk][plane][cout][8]
-            raw = blob.view(np.uint8).ravel()
             op["wtc_off"] = off
-            parts.append(raw)
-            off += raw.size
+            for n0 in range(0, cout, 128):                                  # output blocks of <= 128 channels
+                nb = min(128, cout - n0)
+                planes = [a[:, :, n0:n0 + nb].reshape(taps, ncb, kb // 8, 8, nb).transpose(0, 1, 2, 4, 3) for a in (hi, lo)]
+                raw = np.ascontiguousarray(np.stack(planes, axis=3)).view(np.uint8).ravel()   # [tap][cb][chunk][plane][n][8]
+                parts.append(raw)
+                off += raw.size
             pad = (-off) % 128
             if pad:
                 parts.append(np.zeros(pad, np.uint8))
@@ -375,79 +393,86 @@ def _fold_bn(w: np.ndarray, sd: dict, bn: str, eps: float = 1e-5):
 
 
 def build_classifier_plan(state_dict: dict, in_size: int = 64, mean: float = 0.18, std: float = 0.34) -> Plan:
-    """torchvision ShuffleNetV2 x1.0 (shufflenetv2.py) -> plan.  fp32 activations.
-    channel_shuffle(cat[a, b], 2) == a to even channels, b to odd channels: expressed as
-    stride-2 channel stores of the two producers."""
+    """torchvision ShuffleNetV2 x1.0 (shufflenetv2.py) -> plan, split-f16 activations so that the 1x1
+    convs run on the tensor-core kernel.
+
+    A stage tensor with 2h logical channels is stored as two halves of h channels, each padded to a
+    multiple of 16 (58->64, 116->128, 232->240): logical channel l lives at physical (l // h) * hp + l % h.
+    ``chunk`` is then a contiguous physical view, and ``channel_shuffle(cat[a, b], 2)`` (a to even, b to
+    odd logical channels) is the store pattern of the two producers (lp_op_desc.out_seg_len/out_seg_pad).
+    Padding channels are never written and stay zero (the workspace is zero-initialised)."""
     sd = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state_dict.items()}
     P = Plan()
-    F32, RELU, NONE = L.FMT_F32, L.ACT_RELU, L.ACT_NONE
+    RELU, NONE, G = L.ACT_RELU, L.ACT_NONE, 16
     S = in_size
     img = View(P.buf(S, S, 3, L.FMT_U8), (0,), (3,), False)
     w, b = _fold_bn(sd["conv1.0.weight"], sd, "conv1.1")
     h = S // 2
-    x = P.new_view(h, h, [w.shape[0]], F32)
+    x = P.new_view(h, h, [w.shape[0]], gran=G)
     P.conv("conv1", w, b, img, x, 2, RELU, kind=L.OP_STEM_U8, in_mean=mean, in_std=std)
     h //= 2
-    y = P.new_view(h, h, [x.logical], F32)
+    y = P.new_view(h, h, [x.logical], gran=G)
     P.simple(L.OP_MAXPOOL, "maxpool", x, y, ksize=3, stride=2)
-    x = y
+    x = y                                              # View: segments of the current feature map
 
     def dw(name, prefix_conv, prefix_bn, src, stride):
         wdw, bdw = _fold_bn(sd[prefix_conv + ".weight"], sd, prefix_bn)        # [C,1,3,3]
         c = wdw.shape[0]
+        assert c == src.logical
         hs = P.bufs[src.buf]["h"]
         ho = (hs + 2 - 3) // stride + 1
-        dst = P.new_view(ho, ho, [c], F32)
-        P.simple(L.OP_DWCONV3, name, src, dst, ksize=3, stride=stride,
-                 w=wdw.reshape(c, 9).T.copy(), b=bdw)
+        dst = P.new_view(ho, ho, list(src.lens), gran=G)                          # same segment structure
+        cm = src.chan_map()
+        wp = np.zeros((9, src.phys), np.float32)
+        bp = np.zeros(src.phys, np.float32)
+        wp[:, cm] = wdw.reshape(c, 9).T
+        bp[cm] = bdw
+        P.simple(L.OP_DWCONV3, name, src, dst, ksize=3, stride=stride, w=wp, b=bp)
         P.macs[-1] = ho * ho * 9 * c
         return dst
 
-    def pw(name, prefix_conv, prefix_bn, src, dst, cstride=1):
+    def pw(name, prefix_conv, prefix_bn, src, dst, seg=None):
         wp, bp = _fold_bn(sd[prefix_conv + ".weight"], sd, prefix_bn)
-        P.conv(name, wp, bp, src, dst, 1, RELU, out_cstride=cstride)
+        P.conv(name, wp, bp, src, dst, 1, RELU, out_cstride=2 if seg else 1, seg=seg)
 
     stage = 2
     while f"stage{stage}.0.branch2.0.weight" in sd:
         u = 0
         while f"stage{stage}.{u}.branch2.0.weight" in sd:
             pre = f"stage{stage}.{u}"
-            cin = x.logical
+            hh = P.bufs[x.buf]["h"]
             if u == 0:                                  # down-sampling unit: both branches see all channels
                 bf = sd[pre + ".branch2.5.weight"].shape[0]
-                ho = (P.bufs[x.buf]["h"] + 2 - 3) // 2 + 1
-                out = P.new_view(ho, ho, [2 * bf], F32)
-                even = View(out.buf, (0,), (bf,), False)
-                odd = View(out.buf, (1,), (bf,), False)
+                ho = (hh + 2 - 3) // 2 + 1
+                out = P.new_view(ho, ho, [bf, bf], gran=G)
+                hp = pad_to(bf, G)
                 t = dw(pre + ".branch1.dw", pre + ".branch1.0", pre + ".branch1.1", x, 2)
-                pw(pre + ".branch1.pw", pre + ".branch1.2", pre + ".branch1.3", t, even, 2)
-                t = P.new_view(P.bufs[x.buf]["h"], P.bufs[x.buf]["h"], [bf], F32)
+                pw(pre + ".branch1.pw", pre + ".branch1.2", pre + ".branch1.3", t, out, seg=(0, bf, hp))
+                t = P.new_view(hh, hh, [bf], gran=G)
                 pw(pre + ".branch2.pw1", pre + ".branch2.0", pre + ".branch2.1", x, t)
                 t = dw(pre + ".branch2.dw", pre + ".branch2.3", pre + ".branch2.4", t, 2)
-                pw(pre + ".branch2.pw2", pre + ".branch2.5", pre + ".branch2.6", t, odd, 2)
+                pw(pre + ".branch2.pw2", pre + ".branch2.5", pre + ".branch2.6", t, out, seg=(1, bf, hp))
             else:                                       # basic unit: x1 passes through, x2 -> branch2
-                bf = cin // 2
-                hh = P.bufs[x.buf]["h"]
-                out = P.new_view(hh, hh, [cin], F32)
-                even = View(out.buf, (0,), (bf,), False)
-                odd = View(out.buf, (1,), (bf,), False)
-                x1 = View(x.buf, (0,), (bf,), False)
-                x2 = View(x.buf, (bf,), (bf,), False)
-                P.simple(L.OP_COPY, pre + ".passthrough", x1, even, out_cstride=2)
-                t = P.new_view(hh, hh, [bf], F32)
+                bf = x.logical // 2
+                hp = pad_to(bf, G)
+                out = P.new_view(hh, hh, [bf, bf], gran=G)
+                x1, x2 = x.seg(0), x.seg(1)
+                P.simple(L.OP_COPY, pre + ".passthrough", x1, out, out_cstride=2, seg=(0, bf, hp))
+                t = P.new_view(hh, hh, [bf], gran=G)
                 pw(pre + ".branch2.pw1", pre + ".branch2.0", pre + ".branch2.1", x2, t)
                 t = dw(pre + ".branch2.dw", pre + ".branch2.3", pre + ".branch2.4", t, 1)
-                pw(pre + ".branch2.pw2", pre + ".branch2.5", pre + ".branch2.6", t, odd, 2)
+                pw(pre + ".branch2.pw2", pre + ".branch2.5", pre + ".branch2.6", t, out, seg=(1, bf, hp))
             x = out
             u += 1
         stage += 1
     w5, b5 = _fold_bn(sd["conv5.0.weight"], sd, "conv5.1")
     hh = P.bufs[x.buf]["h"]
-    y = P.new_view(hh, hh, [w5.shape[0]], F32)
+    y = P.new_view(hh, hh, [w5.shape[0]], gran=G)
     P.conv("conv5", w5, b5, x, y, 1, RELU)
     fcw, fcb = sd["fc.weight"], sd["fc.bias"]                       # [C, 1024]
     P.ops.append(dict(kind=L.OP_MEAN_FC, in_buf=y.buf, in_coff=0, cin=fcw.shape[1], out_buf=-1, out_coff=0,
-                      cout=fcw.shape[0], out_cstride=1, res_buf=-1, res_coff=0, ksize=1, stride=1, act=NONE,
+                      cout=fcw.shape[0], out_cstride=1, cout_real=fcw.shape[0], out_seg_len=0, out_seg_pad=0,
+                      res_buf=-1, res_coff=0, ksize=1, stride=1, act=NONE,
                       row_off=0, in_mean=0.0, in_std=1.0, w_off=P._push(fcw.T.copy()), b_off=P._push(fcb), wtc_off=-1))
     P.names.append("mean_fc")
     P.macs.append(fcw.size)
