@@ -62,7 +62,7 @@ struct TcParams {
     int n_mma, mtab_bytes;     // MMA issue table: one uint2 per tcgen05.mma of a tile
     int fills_per_tile;        // streaming weights: n_kb / w_stages (stage pattern repeats every tile)
     int epi_pitch, epi_bytes;  // epilogue staging: bytes per pixel row (+16 pad) and total (0 = direct stores)
-    int tab_bytes;             // 3x3: per-item geometry table (py | px<<6 | chunk<<12 | slot<<18) in shared memory
+    int tab_bytes;             // 3x3: per-slot geometry table (py | px<<8) in shared memory
     int tmem_cols, acc_stride;  // TMEM columns allocated; column stride between the two accumulator stages
     unsigned magic_chunks, magic_pitch;   // ceil(2^32 / n) for division by n_chunks / pitch
     long long total_pix;       // 1x1: n_img*H*W
@@ -222,9 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         const int lt = threadIdx.x - W_LOADER0 * 32;
         const int items_per_plane = n_chunks * p.slots;
         if (p.ksize == 3) {
-            for (int e = lt; e < items_per_plane; e += LOADER_THREADS) {
-                const int slot = (int)__umulhi((unsigned)e, p.magic_chunks);       // e / n_chunks
-                const int chunk = e - slot * n_chunks;
+            for (int slot = lt; slot < p.slots; slot += LOADER_THREADS) {
                 int py, px;
                 if (p.stride == 1) {
                     py = slot / p.pitch;
@@ -235,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                     py = 2 * sr + (ph >> 1);
                     px = 2 * sc + (ph & 1);
                 }
-                tab[e] = (uint32_t)py | ((uint32_t)px << 6) | ((uint32_t)chunk << 12) | ((uint32_t)slot << 18);
+                tab[slot] = (uint32_t)py | ((uint32_t)px << 8);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(LOADER_THREADS) : "memory");      // loaders only
         }
@@ -280,9 +278,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 const __half* base = in_c + (long long)tc.img * p.in_img;
                 const int y_base = tc.oy0 * p.stride - 1, x_base = tc.ox0 * p.stride - 1;
                 for (int e = lt; e < items_per_plane; e += LOADER_THREADS) {
-                    const uint32_t t = tab[e];
-                    const int iy = y_base + (int)(t & 63), ix = x_base + (int)((t >> 6) & 63);
-                    const uint32_t chunk = (t >> 12) & 63, slot = t >> 18;
+                    const uint32_t slot = __umulhi((unsigned)e, p.magic_chunks);       // e / n_chunks
+                    const uint32_t chunk = (uint32_t)e - slot * (uint32_t)n_chunks;
+                    const uint32_t t = tab[slot];
+                    const int iy = y_base + (int)(t & 255), ix = x_base + (int)(t >> 8);
                     const bool valid = ((unsigned)iy < (unsigned)p.H) && ((unsigned)ix < (unsigned)p.W);
                     const __half* src = base + (valid ? (iy * p.W + ix) * p.in_C : 0) + chunk * 8;
                     const uint32_t dst = dst0 + (chunk * p.slots_p + slot) * 16;
@@ -665,31 +664,25 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     p.H = ib.h; p.W = ib.w; p.n_img = batch; p.ksize = op.ksize; p.stride = op.stride;
     p.Ho = (ib.h + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1;
     p.Wo = (ib.w + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1;
-    p.kb_ch = 0;
-    for (int d : {64, 48, 32, 16}) if (op.cin % d == 0) { p.kb_ch = d; break; }     // same rule as plan.py pack_tc_weights
-    if (!p.kb_ch) return 0;
-    p.n_cb = op.cin / p.kb_ch;
     const int taps = op.ksize * op.ksize;
-    p.n_kb = taps * p.n_cb;
     if (op.ksize == 1) { p.slots = TILE_M; p.pitch = 8; }
     else if (op.stride == 1) { p.pitch = TCT_W + 2; p.slots = (TCT_H + 2) * p.pitch; }
     else { p.pitch = TCT_W + 1; p.phase_slots = (TCT_H + 1) * p.pitch; p.slots = 4 * p.phase_slots; }
     p.slots_p = p.slots + ((9 - (p.slots & 7)) & 7);                 // == 1 (mod 8): conflict-free chunk stride
     p.magic_chunks = magic_u32(op.cin / 8);
     p.magic_pitch = magic_u32(p.pitch);
-    p.stage_bytes = p.kb_ch * p.cout * 4;                            // 2 planes x kb_ch x cout x 2 B
     const size_t patch_bytes = (size_t)2 * (op.cin / 8) * p.slots_p * 16;
-    p.tab_bytes = op.ksize == 3 ? ((op.cin / 8) * p.slots * 4 + 127) / 128 * 128 : 0;
+    p.tab_bytes = op.ksize == 3 ? (p.slots * 4 + 127) / 128 * 128 : 0;
     if (op.ksize == 1 && ib.image_bytes != (int64_t)ib.h * ib.w * ib.c * 2) return 0;
-    p.n_mma = p.n_kb * (p.kb_ch / 16) * 2;
-    p.mtab_bytes = (p.n_mma * 8 + 127) / 128 * 128;
+    p.n_mma = taps * (op.cin / 16) * 2;
+    p.mtab_bytes = 0;
     const int out_row_bytes = nb * (ob.fmt == LP_FMT_SPLIT16 ? 2 : 4);
     p.epi_pitch = out_row_bytes + 16;
     const size_t epi_full = (size_t)(ob.fmt == LP_FMT_SPLIT16 ? 2 : 1) * TILE_M * p.epi_pitch + TILE_M * 8;
     const size_t total = 220 * 1024 - 512 - p.tab_bytes - p.mtab_bytes;
-    const size_t w_all = (size_t)p.n_kb * p.stage_bytes;
+    const size_t w_all = (size_t)taps * op.cin * nb * 4;
     // Shared-memory plan.  Weights: resident if the whole layer fits beside >= 2 patch stages, else a ring
-    // whose stage count divides n_kb (so the stage pattern is identical for every tile).  Epilogue staging
+    // of 2-4 stages.  Epilogue staging
     // (coalesced stores) if >= 2 patch stages still fit.  Everything left goes to patch stages.
     auto plan = [&](bool stage_epi) -> bool {
         const size_t budget = total - (stage_epi ? epi_full : 0);
@@ -701,10 +694,9 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
             if (min_ps * patch_bytes + 2 * (size_t)p.stage_bytes > budget) return false;
             int cap = (int)((budget - min_ps * patch_bytes) / p.stage_bytes);
             if (cap > 4) cap = 4;
-            int ws = 0;
-            for (int d = cap; d >= 2; --d) if (p.n_kb % d == 0) { ws = d; break; }
-            if (!ws) return false;
-            p.w_stages = ws;
+            if (cap > p.n_kb) cap = p.n_kb;
+            if (cap < 2) return false;
+            p.w_stages = cap;
         }
         const size_t left = budget - (size_t)p.w_stages * p.stage_bytes;
         int ps = (int)(left / patch_bytes);
@@ -713,7 +705,16 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         p.epi_bytes = stage_epi ? (int)epi_full : 0;
         return !stage_epi || p.patch_stages >= 2;
     };
-    if (!((!seg && plan(true)) || plan(false))) return 0;
+    // K-block size: the packed weights are [tap][8-channel chunk][plane][n][8], so any multiple of 16 that
+    // divides Cin is a valid block; take the largest whose ring fits
+    bool ok = false;
+    for (int d : {64, 48, 32, 16}) {
+        if (op.cin % d) continue;
+        p.kb_ch = d; p.n_cb = op.cin / d; p.n_kb = taps * p.n_cb;
+        p.stage_bytes = d * nb * 4;                                  // 2 planes x kb_ch x cout x 2 B
+        if ((!seg && plan(true)) || plan(false)) { ok = true; break; }
+    }
+    if (!ok) return 0;
     p.fills_per_tile = p.resident ? 0 : p.n_kb / p.w_stages;
     p.acc_stride = 2 * nb < 32 ? 32 : 2 * nb;        // [Ahi*Bhi+Alo*Bhi | Ahi*Blo]
     p.acc_stages = 512 / p.acc_stride > MAX_AST ? MAX_AST : 512 / p.acc_stride;
