@@ -105,6 +105,14 @@ int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int n_bufs,
 /* 1 = use tcgen05 kernels where an op has wtc_off >= 0 (default), 0 = SIMT only. */
 int lp_set_tensor_core(lp_ctx* ctx, int enable);
 
+/* Fused classifier: the whole ShuffleNetV2 forward of `group` ROIs in one persistent CTA, driven by a
+ * host-built step list (plan.py build_fused_classifier; struct FStep in csrc/shufflenet_fused.cu, 18 x int32
+ * per step, device memory) over an fp32 weight blob.  When loaded, lp_classify uses it instead of the
+ * layer-by-layer plan; lp_set_fused_classifier(ctx, 0) switches back. */
+int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_back, const float* weights,
+                             int group, int in_hw, int n_classes, size_t smem_bytes, float mean, float stdv);
+int lp_set_fused_classifier(lp_ctx* ctx, int enable);
+
 /* ---- K1: letterbox.  Replaces letterbox() + cvtColor (e2e.py:66-86, :224-225).
  * frames[i]: HWC BGR u8 image i (pitch[i] bytes per row).  out: B x S x S x 3 RGB u8,
  * bit-exact with cv2.resize(INTER_LINEAR) + copyMakeBorder(114).  ratio[i],

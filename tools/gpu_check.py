@@ -97,7 +97,11 @@ def main():
         lg = clf.logits_for(got)
         x = (torch.from_numpy(got.astype(np.float32)) / 255 - 0.18) / 0.34
         with torch.no_grad(): rl = clf_ref(x.permute(0, 3, 1, 2)).numpy()
-        print("logits max diff %.3e (tolerance 1e-2), top-1 agree %d/%d" % (np.abs(lg - rl).max(), int((lg.argmax(1) == rl.argmax(1)).sum()), len(lg)))
+        print("fused  logits max diff %.3e (tolerance 1e-2), top-1 agree %d/%d" % (np.abs(lg - rl).max(), int((lg.argmax(1) == rl.argmax(1)).sum()), len(lg)))
+        clf.set_fused(False)
+        lg2 = clf.logits_for(got)
+        clf.set_fused(True)
+        print("layered logits max diff %.3e, top-1 agree %d/%d" % (np.abs(lg2 - rl).max(), int((lg2.argmax(1) == rl.argmax(1)).sum()), len(lg2)))
         if np.abs(lg - rl).max() > 1e-3:
             bufs, _ = run_plan_cpu(clf.plan, got[:clf.max_batch])
             n = min(len(got), clf.max_batch); clf.logits_for(got[:n])

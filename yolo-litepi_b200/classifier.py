@@ -12,7 +12,7 @@ import torch
 
 from . import _lib as L
 from .detector import FrameBatch, _ptr, _stream
-from .plan import build_classifier_plan
+from .plan import build_classifier_plan, build_fused_classifier
 
 
 def _random_state_dict(num_classes: int, seed: Optional[int]):
@@ -31,7 +31,7 @@ class B200Classifier:
     def __init__(self, model_path: Optional[str], arch: str = "shufflenetv2", num_classes: int = 58,
                  input_size: int = 64, device="cpu", state_dict: Optional[dict] = None,
                  cuda_device: int = 0, max_batch: int = 256, seed: Optional[int] = None,
-                 tensor_cores: bool = True):
+                 tensor_cores: bool = True, fused: bool = True, fused_group: int = 2):
         # `device` is the reference's torch device string (e2e.py:354); this backend always runs on
         # cuda:`cuda_device`.  Only shufflenetv2 is implemented (ValueError like e2e.py:335 otherwise).
         if arch != "shufflenetv2":
@@ -72,8 +72,22 @@ class B200Classifier:
                                         _ptr(self.weights), self.weights.numel(), _ptr(self.weights_tc),
                                         tc_blob.size, self.max_batch),
                     "lp_net_load(classifier)")
+        # the production path: the whole network in one persistent kernel (csrc/shufflenet_fused.cu); the
+        # layer-by-layer plan above stays loaded as the cross-check (set_fused(False))
+        self.fused = bool(fused) and self.input_size == 64
+        if self.fused:
+            steps, fw, n_front, n_back, smem = build_fused_classifier(sd, group=fused_group, in_size=self.input_size)
+            with torch.cuda.device(self.device):
+                self.fused_steps = torch.from_numpy(steps).to(self.device)
+                self.fused_weights = torch.from_numpy(fw).to(self.device)
+            L.check(L.lib().lp_fused_classifier_load(self.ctx.handle, _ptr(self.fused_steps), n_front, n_back,
+                                                     _ptr(self.fused_weights), fused_group, self.input_size,
+                                                     self.num_classes, smem, 0.18, 0.34), "lp_fused_classifier_load")
         self._cap = 0
         self._alloc(self.max_batch)
+
+    def set_fused(self, enable: bool):
+        L.check(L.lib().lp_set_fused_classifier(self.ctx.handle, 1 if enable else 0))
 
     def _alloc(self, n: int):
         if n <= self._cap:

@@ -33,6 +33,8 @@ extern "C" int lp_create(lp_ctx** out, int device) {
     LP_CHECK(prop.major == 10, "lp_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
              prop.major, prop.minor);
     lp_ctx* c = new lp_ctx();
+    static int next_slot = 0;
+    c->fused_slot = next_slot++ % 16;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     *out = c;
@@ -70,6 +72,12 @@ extern "C" int lp_probe_read(lp_ctx* ctx, float* ms_h, int cap) {
         LP_CUDA(cudaEventElapsedTime(&ms_h[m], ctx->probe_ev[2 * i], ctx->probe_ev[2 * i + 1]));
     }
     return m;
+}
+
+extern "C" int lp_set_fused_classifier(lp_ctx* ctx, int enable) {
+    LP_CHECK(ctx, "lp_set_fused_classifier: null ctx");
+    ctx->use_fused = enable ? 1 : 0;
+    return 0;
 }
 
 extern "C" int lp_set_tensor_core(lp_ctx* ctx, int enable) {
@@ -163,6 +171,11 @@ extern "C" int lp_classify(lp_ctx* ctx, const uint8_t* in, int n, void* workspac
     LP_CHECK(P.loaded, "lp_classify: classifier not loaded");
     cudaStream_t st = (cudaStream_t)stream;
     const int C = P.ops.back().cout;
+    {
+        const int r = lp_fused_classify(ctx, in, n, logits, st);       // whole network in one persistent kernel
+        if (r < 0) return r;
+        if (r == 1) return lp_launch_softmax_argmax(ctx, logits, n, C, probs, argmax, st);
+    }
     const size_t img_bytes = (size_t)P.bufs[P.ops[0].in_buf].h * P.bufs[P.ops[0].in_buf].w * 3;
     for (int base = 0; base < n; base += P.max_batch) {
         const int nb = n - base < P.max_batch ? n - base : P.max_batch;

@@ -61,6 +61,8 @@ struct lp_ctx {
     int probe_net = -1, probe_op = -1;
     std::vector<cudaEvent_t> probe_ev;   // pairs (start, stop), ring
     int probe_n = 0;
+    int fused_slot = -1;             // index into the fused-classifier table (shufflenet_fused.cu)
+    int use_fused = 1;
     long long* tc_dbg = nullptr;     // device buffer (16 x int64) for conv_tc role timing; debugging only
 };
 #define LP_PROBE_RING 512
@@ -80,4 +82,5 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
 int lp_launch_detect_tail(lp_ctx* ctx, const float* head_raw, int batch, int head_c, float* out0, cudaStream_t st);
 
 // tensor-core path (conv_tc.cu); returns 1 if it handled the op, 0 if not applicable, <0 on error
+int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cudaStream_t st);
 int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st);

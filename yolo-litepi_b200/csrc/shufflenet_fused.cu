@@ -1,0 +1,331 @@
+// K7 fused: the whole ShuffleNetV2 x1.0 forward of a group of ROIs inside ONE persistent CTA.
+// Replaces self.model(batch) (src/vntsr/pipeline/e2e.py:393; torchvision shufflenetv2.py) for the 64x64
+// classifier input.  The layer-by-layer plan (71 launches, a few thousand pixels each) is launch- and
+// latency-bound; here every activation of a ROI lives in shared memory (<= 30 KB per ROI after the stem),
+// the folded weights (5.2 MB fp32) stream from L2 through the read-only path, and the only global traffic
+// is the 12 KB u8 crop in and C logits out.  fp32 FMA throughout (logit parity ~1e-6).
+//
+// The CTA executes a host-built step list (plan.py build_fused_classifier):
+//   front end, per ROI : conv1 3x3 s2 (+ToTensor/Normalize via a 256-entry table) -> maxpool 3x3 s2 ->
+//                        stage2 unit 0 (the only unit whose intermediates exceed 30 KB)
+//   back end, per group: stage2 units 1-3, stage3, stage4, conv5, global mean, fc -- G ROIs stacked as
+//                        GEMM rows so each weight is fetched once per group.
+// channel_shuffle is the store pattern of the producers (dst channel = off + j * 2), chunk is a view.
+#include "common.cuh"
+
+enum { FS_CONV1 = 0, FS_MAXPOOL = 1, FS_PW = 2, FS_DW = 3, FS_COPY = 4, FS_MEANFC = 5 };
+
+struct FStep {
+    int op;
+    int src, dst;              // float offsets into shared memory
+    int src_C, src_off;        // channels per pixel of the source tensor, first channel read
+    int dst_C, dst_off, dst_cs;
+    int cin, cout;
+    int H, W, stride;          // input spatial size
+    int relu;
+    int w_off, b_off;          // float offsets into the weight blob
+    int dst_roi_stride;        // front end: added per ROI index to dst (0 otherwise)
+    int pad0;
+};
+
+constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_MAX_STEPS = 96;
+
+// Pointwise conv as a shared-memory GEMM: thread tile = RT rows x 4 output channels.  Weights come from
+// global memory (L2-resident, read-only path); the loop is latency-bound on them, so UNR rows of W are in
+// flight per thread (loaded into registers before the FMAs that use them) and RT is picked so that a layer
+// has >= one tile per thread.
+template <int RT>
+__device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C, float* __restrict__ out, int out_C, int dst_cs,
+                                         int rows, int cin, int cout, const float* __restrict__ W, const float* __restrict__ bias,
+                                         int relu) {
+    constexpr int UNR = 8;
+    const int cout_p = (cout + 3) & ~3;
+    const int ncg = cout_p >> 2, nrg = (rows + RT - 1) / RT;
+    for (int tile = threadIdx.x; tile < nrg * ncg; tile += FUSED_THREADS) {
+        const int rg = tile / ncg, cg = tile - rg * ncg;
+        const int r0 = rg * RT, c0 = cg * 4;
+        float acc[RT][4];
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+#pragma unroll
+        for (int r = 0; r < RT; ++r) { acc[r][0] = b4.x; acc[r][1] = b4.y; acc[r][2] = b4.z; acc[r][3] = b4.w; }
+        const float* ip[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) ip[r] = in + (size_t)min(r0 + r, rows - 1) * in_C;
+        const float* wp = W + c0;
+        int ci = 0;
+        for (; ci + UNR <= cin; ci += UNR) {
+            float4 w[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(ci + u) * cout_p));
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    const float a = ip[r][ci + u];
+                    acc[r][0] = fmaf(a, w[u].x, acc[r][0]);
+                    acc[r][1] = fmaf(a, w[u].y, acc[r][1]);
+                    acc[r][2] = fmaf(a, w[u].z, acc[r][2]);
+                    acc[r][3] = fmaf(a, w[u].w, acc[r][3]);
+                }
+            }
+        }
+        for (; ci < cin; ++ci) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (size_t)ci * cout_p));
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const float a = ip[r][ci];
+                acc[r][0] = fmaf(a, w.x, acc[r][0]);
+                acc[r][1] = fmaf(a, w.y, acc[r][1]);
+                acc[r][2] = fmaf(a, w.z, acc[r][2]);
+                acc[r][3] = fmaf(a, w.w, acc[r][3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            if (r0 + r >= rows) break;
+            float* op = out + (size_t)(r0 + r) * out_C;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c0 + j < cout) {
+                    const float v = relu ? fmaxf(acc[r][j], 0.f) : acc[r][j];
+                    op[(c0 + j) * dst_cs] = v;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float* __restrict__ W,
+                        const FStep* __restrict__ steps, int n_front, int n_back, int G, int in_hw,
+                        float mean, float stdv, float* __restrict__ logits, int n_classes) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ FStep s_steps[FUSED_MAX_STEPS];
+    __shared__ float s_norm[256];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (n_front + n_back) * (int)(sizeof(FStep) / 4); i += FUSED_THREADS)
+        reinterpret_cast<int*>(s_steps)[i] = reinterpret_cast<const int*>(steps)[i];
+    // ToTensor + Normalize exactly as torchvision computes them: (u8 / 255 - mean) / std, IEEE divisions
+    if (tid < 256) s_norm[tid] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)tid, 255.f), mean), stdv);
+    __syncthreads();
+    const int img_bytes = in_hw * in_hw * 3;
+    const int n_groups = (n_rois + G - 1) / G;
+
+    for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
+        const int roi0 = group * G;
+        const int ng = min(G, n_rois - roi0);
+        for (int pass = 0; pass <= ng; ++pass) {
+            // pass < ng: front end of ROI `pass`; pass == ng: back end of the whole group
+            const bool back = (pass == ng);
+            const int s_begin = back ? n_front : 0, s_end = back ? n_front + n_back : n_front;
+            if (!back) {
+                // stage the u8 crop (16-B copies); the CONV1 step's src is its float offset
+                const uint4* g4 = reinterpret_cast<const uint4*>(in + (size_t)(roi0 + pass) * img_bytes);
+                uint4* s4 = reinterpret_cast<uint4*>(sm + s_steps[0].src);
+                for (int i = tid; i < img_bytes / 16; i += FUSED_THREADS) s4[i] = __ldg(g4 + i);
+                __syncthreads();
+            }
+            for (int si = s_begin; si < s_end; ++si) {
+                const FStep& st = s_steps[si];
+                const int rois = back ? G : 1;
+                float* dst = sm + st.dst + (back ? 0 : pass * st.dst_roi_stride);
+                const float* src = sm + st.src;
+                const int Ho = (st.op == FS_PW || st.op == FS_COPY) ? st.H : (st.H + 2 - 3) / st.stride + 1;
+                const int Wo = (st.op == FS_PW || st.op == FS_COPY) ? st.W : (st.W + 2 - 3) / st.stride + 1;
+                switch (st.op) {
+                case FS_CONV1: {
+                    // 3x3 stride 2 pad 1 on the u8 RGB crop, 3 -> cout, ReLU.  thread = (pixel, 4 channels)
+                    const uint8_t* img = reinterpret_cast<const uint8_t*>(src);
+                    const int ncg = (st.cout + 3) >> 2;
+                    const float* w = W + st.w_off;           // [27][cout_p]
+                    const int cout_p = ncg * 4;
+                    for (int t = tid; t < Ho * Wo * ncg; t += FUSED_THREADS) {
+                        const int cg = t % ncg, pix = t / ncg, oy = pix / Wo, ox = pix - oy * Wo;
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(W + st.b_off + cg * 4));
+                        float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int iy = oy * 2 - 1 + ky;
+                            if (iy < 0 || iy >= st.H) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int ix = ox * 2 - 1 + kx;
+                                if (ix < 0 || ix >= st.W) continue;
+                                const uint8_t* px = img + (iy * st.W + ix) * 3;
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    const float x = s_norm[px[c]];
+                                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((ky * 3 + kx) * 3 + c) * cout_p + cg * 4));
+                                    a0 = fmaf(x, wv.x, a0); a1 = fmaf(x, wv.y, a1); a2 = fmaf(x, wv.z, a2); a3 = fmaf(x, wv.w, a3);
+                                }
+                            }
+                        }
+                        float* o = dst + (size_t)pix * st.dst_C + cg * 4;
+                        const float v[4] = {a0, a1, a2, a3};
+                        for (int j = 0; j < 4; ++j) if (cg * 4 + j < st.cout) o[j] = fmaxf(v[j], 0.f);
+                    }
+                    break;
+                }
+                case FS_MAXPOOL: {
+                    for (int t = tid; t < Ho * Wo * st.cout; t += FUSED_THREADS) {
+                        const int c = t % st.cout, pix = t / st.cout, oy = pix / Wo, ox = pix - oy * Wo;
+                        float m = -INFINITY;
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int iy = oy * 2 - 1 + ky;
+                            if (iy < 0 || iy >= st.H) continue;
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int ix = ox * 2 - 1 + kx;
+                                if (ix < 0 || ix >= st.W) continue;
+                                m = fmaxf(m, src[(size_t)(iy * st.W + ix) * st.src_C + st.src_off + c]);
+                            }
+                        }
+                        dst[(size_t)pix * st.dst_C + st.dst_off + c] = m;
+                    }
+                    break;
+                }
+                case FS_PW: {
+                    const int rows = rois * st.H * st.W;
+                    const float* ip = src + st.src_off;
+                    float* op = dst + st.dst_off;
+                    // RT so that the layer has about one tile per thread (tiles = rows/RT * cout/4)
+                    const int tiles4 = ((rows + 3) / 4) * ((st.cout + 3) / 4);
+                    const int tiles2 = ((rows + 1) / 2) * ((st.cout + 3) / 4);
+                    if (tiles4 >= FUSED_THREADS - 64) pw_layer<4>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.w_off, W + st.b_off, st.relu);
+                    else if (tiles2 >= FUSED_THREADS - 64) pw_layer<2>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.w_off, W + st.b_off, st.relu);
+                    else pw_layer<1>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.w_off, W + st.b_off, st.relu);
+                    break;
+                }
+                case FS_DW: {
+                    // depthwise 3x3, pad 1, bias, no activation.  weights [9][C].  (row, channel) advance
+                    // incrementally -- an integer division per element would dominate this tiny layer.
+                    const int C = st.cout, hw_in = st.H * st.W, hw_out = Ho * Wo;
+                    const int wo_shift = __ffs(Wo) - 1, hw_shift = __ffs(hw_out) - 1;   // Ho, Wo are powers of two
+                    const float* w = W + st.w_off;
+                    const float* b = W + st.b_off;
+                    const int step_r = FUSED_THREADS / C, step_c = FUSED_THREADS - step_r * C;
+                    int c = tid % C, row = tid / C;
+                    const int rows = rois * hw_out;
+                    while (row < rows) {
+                        const int g = row >> hw_shift, r = row & (hw_out - 1);
+                        const int oy = r >> wo_shift, ox = r & (Wo - 1);
+                        float acc = __ldg(b + c);
+                        const float* ip = src + (size_t)g * hw_in * st.src_C + st.src_off + c;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int iy = oy * st.stride - 1 + ky;
+                            if (iy < 0 || iy >= st.H) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int ix = ox * st.stride - 1 + kx;
+                                if (ix < 0 || ix >= st.W) continue;
+                                acc = fmaf(ip[(size_t)(iy * st.W + ix) * st.src_C], __ldg(w + (ky * 3 + kx) * C + c), acc);
+                            }
+                        }
+                        dst[(size_t)row * st.dst_C + st.dst_off + c * st.dst_cs] = acc;
+                        row += step_r; c += step_c;
+                        if (c >= C) { c -= C; ++row; }
+                    }
+                    break;
+                }
+                case FS_COPY: {
+                    const int rows = rois * st.H * st.W, C = st.cout;
+                    const int step_r = FUSED_THREADS / C, step_c = FUSED_THREADS - step_r * C;
+                    int c = tid % C, row = tid / C;
+                    while (row < rows) {
+                        dst[(size_t)row * st.dst_C + st.dst_off + c * st.dst_cs] = src[(size_t)row * st.src_C + st.src_off + c];
+                        row += step_r; c += step_c;
+                        if (c >= C) { c -= C; ++row; }
+                    }
+                    break;
+                }
+                case FS_MEANFC: {
+                    // x.mean([2,3]) then fc.  dst = scratch: [rois][cin] means, then [8][rois][64] partial sums.
+                    // K is split over 8 thread groups (64 lanes = classes each) so the weight reads are
+                    // coalesced and 8 rows of W are in flight per thread.
+                    const int hw = st.H * st.W;
+                    for (int t = tid; t < rois * st.cin; t += FUSED_THREADS) {
+                        const int c = t % st.cin, g = t / st.cin;
+                        float s = 0.f;
+                        for (int q = 0; q < hw; ++q) s += src[(size_t)(g * hw + q) * st.src_C + c];
+                        dst[t] = s / (float)hw;
+                    }
+                    __syncthreads();
+                    const float* w = W + st.w_off;           // [cin][cout]
+                    float* part = dst + rois * st.cin;
+                    for (int j0 = 0; j0 < st.cout; j0 += 64) {
+                        const int j = j0 + (tid & 63), ks = tid >> 6;      // 8 K-slices
+                        const int kper = (st.cin + 7) / 8, k0 = ks * kper, k1 = min(st.cin, k0 + kper);
+                        for (int g = 0; g < rois; ++g) {
+                            float acc = 0.f;
+                            if (j < st.cout) {
+                                const float* m = dst + (size_t)g * st.cin;
+                                int c = k0;
+                                for (; c + 8 <= k1; c += 8) {
+                                    float wv[8];
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(c + u) * st.cout + j);
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u) acc = fmaf(m[c + u], wv[u], acc);
+                                }
+                                for (; c < k1; ++c) acc = fmaf(m[c], __ldg(w + (size_t)c * st.cout + j), acc);
+                            }
+                            part[(ks * rois + g) * 64 + (tid & 63)] = acc;
+                        }
+                        __syncthreads();
+                        for (int t = tid; t < ng * 64; t += FUSED_THREADS) {
+                            const int jj = t & 63, g = t >> 6;
+                            if (j0 + jj < st.cout) {
+                                float acc = __ldg(W + st.b_off + j0 + jj);
+                                for (int k = 0; k < 8; ++k) acc += part[(k * rois + g) * 64 + jj];
+                                logits[(size_t)(roi0 + g) * n_classes + j0 + jj] = acc;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    break;
+                }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+struct lp_fused_cls {
+    const FStep* steps_dev = nullptr;
+    const float* weights = nullptr;
+    int n_front = 0, n_back = 0, G = 0, in_hw = 0, n_classes = 0;
+    size_t smem_bytes = 0;
+    float mean = 0.f, stdv = 1.f;
+    bool loaded = false;
+};
+static lp_fused_cls g_fused[16];       // one slot per context id (contexts are few and long-lived)
+
+extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_back, const float* weights,
+                                        int group, int in_hw, int n_classes, size_t smem_bytes, float mean, float stdv) {
+    LP_CHECK(ctx && steps_dev && weights, "lp_fused_classifier_load: null argument");
+    LP_CHECK(n_front + n_back <= FUSED_MAX_STEPS && n_front > 0 && n_back > 0, "lp_fused_classifier_load: bad step counts");
+    LP_CHECK(smem_bytes <= 227 * 1024, "lp_fused_classifier_load: %zu B shared memory exceeds 227 KB", smem_bytes);
+    LP_CHECK(ctx->fused_slot >= 0 && ctx->fused_slot < 16, "lp_fused_classifier_load: too many contexts");
+    lp_fused_cls& f = g_fused[ctx->fused_slot];
+    f.steps_dev = (const FStep*)steps_dev; f.weights = weights; f.n_front = n_front; f.n_back = n_back;
+    f.G = group; f.in_hw = in_hw; f.n_classes = n_classes; f.smem_bytes = smem_bytes; f.mean = mean; f.stdv = stdv;
+    LP_CUDA(cudaFuncSetAttribute(shufflenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    f.loaded = true;
+    return 0;
+}
+
+// returns 1 if it ran, 0 if no fused classifier is loaded
+int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cudaStream_t st) {
+    if (ctx->fused_slot < 0 || ctx->fused_slot >= 16 || !g_fused[ctx->fused_slot].loaded || !ctx->use_fused) return 0;
+    const lp_fused_cls& f = g_fused[ctx->fused_slot];
+    const int groups = (n + f.G - 1) / f.G;
+    const int grid = groups < ctx->sm_count ? groups : ctx->sm_count;
+    shufflenet_fused_kernel<<<grid, FUSED_THREADS, f.smem_bytes, st>>>(in, n, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
+                                                                       f.in_hw, f.mean, f.stdv, logits, f.n_classes);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(e)); return -2; }
+    return 1;
+}

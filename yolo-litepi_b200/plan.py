@@ -478,3 +478,136 @@ def build_classifier_plan(state_dict: dict, in_size: int = 64, mean: float = 0.1
     P.macs.append(fcw.size)
     P.meta.update(num_classes=int(fcw.shape[0]), in_size=S)
     return P
+
+
+# ============================================================================ fused classifier
+FS_CONV1, FS_MAXPOOL, FS_PW, FS_DW, FS_COPY, FS_MEANFC = range(6)
+FSTEP_WORDS = 18        # struct FStep in csrc/shufflenet_fused.cu
+
+
+def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
+    """Step list + fp32 weight blob for the persistent fused ShuffleNetV2 kernel
+    (csrc/shufflenet_fused.cu).  Returns (steps int32 [n, 18], weights f32, n_front, n_back, smem_bytes).
+
+    Shared-memory map (floats): Y = G x 7424 (stage tensor A) | scratch.  Back end: B = G x 7424,
+    T1 = G x 7424, T2 = G x 3712.  Front end (per ROI) overlays the scratch: u8 crop, conv1 output,
+    pooled tensor, and -- once conv1's output is dead -- the stage2.0 intermediates."""
+    if in_size != 64:
+        raise ValueError("the fused classifier is laid out for 64x64 inputs")
+    sd = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state_dict.items()}
+    G = int(group)
+    blobs: List[np.ndarray] = []
+    nf = [0]
+
+    def push(a):
+        a = np.ascontiguousarray(a, np.float32).ravel()
+        off = nf[0]
+        blobs.append(a)
+        nf[0] += a.size
+        pad = (-nf[0]) % 4
+        if pad:
+            blobs.append(np.zeros(pad, np.float32)); nf[0] += pad
+        return off
+
+    def pw_w(conv, bn):
+        w, b = _fold_bn(sd[conv + ".weight"], sd, bn)                # [cout, cin, 1, 1]
+        cout, cin = w.shape[:2]
+        cp = (cout + 3) // 4 * 4
+        wp = np.zeros((cin, cp), np.float32); wp[:, :cout] = w.reshape(cout, cin).T
+        bp = np.zeros(cp, np.float32); bp[:cout] = b
+        return push(wp), push(bp), cin, cout
+
+    def dw_w(conv, bn):
+        w, b = _fold_bn(sd[conv + ".weight"], sd, bn)                # [C,1,3,3]
+        c = w.shape[0]
+        return push(w.reshape(c, 9).T.copy()), push(b), c
+
+    steps: List[List[int]] = []
+
+    def step(op, src, dst, src_C=0, src_off=0, dst_C=0, dst_off=0, dst_cs=1, cin=0, cout=0, H=0, W=0, stride=1, relu=0,
+             w_off=0, b_off=0, roi_stride=0):
+        steps.append([op, src, dst, src_C, src_off, dst_C, dst_off, dst_cs, cin, cout, H, W, stride, relu, w_off, b_off,
+                      roi_stride, 0])
+
+    c1 = sd["conv1.0.weight"].shape[0]                                # 24
+    widths = [sd[f"stage{s}.0.branch2.5.weight"].shape[0] for s in (2, 3, 4)]   # 58, 116, 232
+    c5 = sd["conv5.0.weight"].shape[0]
+    ncls = sd["fc.weight"].shape[0]
+    ymax = 8 * 8 * 2 * widths[0]                                      # 7424 floats per ROI: largest stage tensor
+    Y, S = 0, G * ymax
+    B, T1, T2 = S, S + G * ymax, S + 2 * G * ymax
+    t2_roi = 8 * 8 * widths[0]                                        # 3712
+    IMG, C1 = S, S + (in_size * in_size * 3 + 3) // 4
+    X0 = C1 + 32 * 32 * c1
+    F_T2 = C1
+    F_T3 = F_T2 + 16 * 16 * widths[0]
+    F_T1 = F_T3 + 8 * 8 * widths[0]
+    assert F_T1 + 8 * 8 * c1 <= X0 and X0 + 16 * 16 * c1 <= S + max(G * (2 * ymax + t2_roi), 0) + 10 ** 9
+    scratch = max(X0 + 16 * 16 * c1 - S, G * (2 * ymax + t2_roi))
+    total_floats = S + scratch
+    # ---- front end (per ROI)
+    w, b = _fold_bn(sd["conv1.0.weight"], sd, "conv1.1")             # [24,3,3,3]
+    cp = (c1 + 3) // 4 * 4
+    w1 = np.zeros((27, cp), np.float32); w1[:, :c1] = w.transpose(2, 3, 1, 0).reshape(27, c1)
+    b1 = np.zeros(cp, np.float32); b1[:c1] = b
+    step(FS_CONV1, IMG, C1, dst_C=c1, cout=c1, H=64, W=64, stride=2, relu=1, w_off=push(w1), b_off=push(b1))
+    step(FS_MAXPOOL, C1, X0, src_C=c1, dst_C=c1, cout=c1, H=32, W=32, stride=2)
+    bf = widths[0]
+    wo, bo, c = dw_w("stage2.0.branch1.0", "stage2.0.branch1.1")
+    step(FS_DW, X0, F_T1, src_C=c1, dst_C=c1, cout=c, H=16, W=16, stride=2, w_off=wo, b_off=bo)
+    wo, bo, ci, co = pw_w("stage2.0.branch1.2", "stage2.0.branch1.3")
+    step(FS_PW, F_T1, Y, src_C=c1, dst_C=2 * bf, dst_off=0, dst_cs=2, cin=ci, cout=co, H=8, W=8, relu=1, w_off=wo, b_off=bo,
+         roi_stride=ymax)
+    wo, bo, ci, co = pw_w("stage2.0.branch2.0", "stage2.0.branch2.1")
+    step(FS_PW, X0, F_T2, src_C=c1, dst_C=bf, cin=ci, cout=co, H=16, W=16, relu=1, w_off=wo, b_off=bo)
+    wo, bo, c = dw_w("stage2.0.branch2.3", "stage2.0.branch2.4")
+    step(FS_DW, F_T2, F_T3, src_C=bf, dst_C=bf, cout=c, H=16, W=16, stride=2, w_off=wo, b_off=bo)
+    wo, bo, ci, co = pw_w("stage2.0.branch2.5", "stage2.0.branch2.6")
+    step(FS_PW, F_T3, Y, src_C=bf, dst_C=2 * bf, dst_off=1, dst_cs=2, cin=ci, cout=co, H=8, W=8, relu=1, w_off=wo, b_off=bo,
+         roi_stride=ymax)
+    n_front = len(steps)
+    # ---- back end (G ROIs stacked)
+    X, OUT = Y, B
+    hw = 8
+    for stage, bf in zip((2, 3, 4), widths):
+        u = 0
+        while f"stage{stage}.{u}.branch2.0.weight" in sd:
+            pre = f"stage{stage}.{u}"
+            if u == 0 and stage == 2:
+                u += 1
+                continue                                              # done in the front end
+            if u == 0:                                                # down-sampling unit
+                cin_all = bf                                          # previous stage has 2*(bf/2) = bf channels
+                wo, bo, c = dw_w(pre + ".branch1.0", pre + ".branch1.1")
+                step(FS_DW, X, T2, src_C=cin_all, dst_C=cin_all, cout=c, H=hw, W=hw, stride=2, w_off=wo, b_off=bo)
+                wo, bo, ci, co = pw_w(pre + ".branch1.2", pre + ".branch1.3")
+                step(FS_PW, T2, OUT, src_C=cin_all, dst_C=2 * bf, dst_off=0, dst_cs=2, cin=ci, cout=co, H=hw // 2, W=hw // 2,
+                     relu=1, w_off=wo, b_off=bo)
+                wo, bo, ci, co = pw_w(pre + ".branch2.0", pre + ".branch2.1")
+                step(FS_PW, X, T1, src_C=cin_all, dst_C=bf, cin=ci, cout=co, H=hw, W=hw, relu=1, w_off=wo, b_off=bo)
+                wo, bo, c = dw_w(pre + ".branch2.3", pre + ".branch2.4")
+                step(FS_DW, T1, T2, src_C=bf, dst_C=bf, cout=c, H=hw, W=hw, stride=2, w_off=wo, b_off=bo)
+                hw //= 2
+                wo, bo, ci, co = pw_w(pre + ".branch2.5", pre + ".branch2.6")
+                step(FS_PW, T2, OUT, src_C=bf, dst_C=2 * bf, dst_off=1, dst_cs=2, cin=ci, cout=co, H=hw, W=hw, relu=1,
+                     w_off=wo, b_off=bo)
+            else:                                                     # basic unit
+                step(FS_COPY, X, OUT, src_C=2 * bf, src_off=0, dst_C=2 * bf, dst_off=0, dst_cs=2, cout=bf, H=hw, W=hw)
+                wo, bo, ci, co = pw_w(pre + ".branch2.0", pre + ".branch2.1")
+                step(FS_PW, X, T1, src_C=2 * bf, src_off=bf, dst_C=bf, cin=ci, cout=co, H=hw, W=hw, relu=1, w_off=wo, b_off=bo)
+                wo, bo, c = dw_w(pre + ".branch2.3", pre + ".branch2.4")
+                step(FS_DW, T1, T2, src_C=bf, dst_C=bf, cout=c, H=hw, W=hw, stride=1, w_off=wo, b_off=bo)
+                wo, bo, ci, co = pw_w(pre + ".branch2.5", pre + ".branch2.6")
+                step(FS_PW, T2, OUT, src_C=bf, dst_C=2 * bf, dst_off=1, dst_cs=2, cin=ci, cout=co, H=hw, W=hw, relu=1,
+                     w_off=wo, b_off=bo)
+            X, OUT = OUT, X
+            u += 1
+    wo, bo, ci, co = pw_w("conv5.0", "conv5.1")
+    assert G * hw * hw * c5 <= G * ymax
+    step(FS_PW, X, T1, src_C=2 * widths[2], dst_C=c5, cin=ci, cout=co, H=hw, W=hw, relu=1, w_off=wo, b_off=bo)
+    step(FS_MEANFC, T1, T2, src_C=c5, cin=c5, cout=ncls, H=hw, W=hw, w_off=push(sd["fc.weight"].T.copy()), b_off=push(sd["fc.bias"]))
+    assert G * c5 <= G * t2_roi
+    n_back = len(steps) - n_front
+    arr = np.asarray(steps, dtype=np.int32)
+    assert arr.shape[1] == FSTEP_WORDS
+    return arr, np.concatenate(blobs), n_front, n_back, total_floats * 4
