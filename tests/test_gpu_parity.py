@@ -252,6 +252,35 @@ def test_classifier_logits_and_top1(clf):
     assert e[0].shape == (0,) and e[1].shape == (0,)
 
 
+@pytest.mark.parametrize("mode", ["fused", "layered_tc", "layered_simt"])
+def test_classifier_paths_agree(lp, mode):
+    """the three classifier execution paths (fused persistent kernel, layer-by-layer plan on the tensor
+    cores, layer-by-layer plan on the SIMT kernels) all reproduce torchvision"""
+    from litepi_b200 import synth
+    ref = PR.build_shufflenet(49, seed=2)
+    c = lp.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=ref.state_dict(), max_batch=32,
+                          tensor_cores=(mode != "layered_simt"), fused=(mode == "fused"))
+    u8 = np.stack([PR.classifier_input_ref(cr)[0] for cr in synth.roi_crops(45, seed=5)])     # 45: ragged last group/chunk
+    lg = c.logits_for(u8)
+    x = (torch.from_numpy(u8.astype(np.float32)) / 255 - 0.18) / 0.34
+    with torch.no_grad():
+        rl = ref(x.permute(0, 3, 1, 2)).numpy()
+    assert np.abs(lg - rl).max() < LOGIT_TOL and np.array_equal(lg.argmax(1), rl.argmax(1))
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_detector_tensor_core_and_simt_paths(lp, v1_paths, tc):
+    det = lp.B200Detector(v1_paths[0], v1_paths[1], max_batch=3, seed=0, tensor_cores=tc)
+    orc = DetectorOracle(v1_paths[0], v1_paths[1], seed=0)
+    _sync(orc, det.model)
+    assert (det.tc_ops > 40) == tc
+    x = np.random.default_rng(9).integers(0, 256, (3, 640, 640, 3), dtype=np.uint8)
+    got = det.forward(x)
+    ref = orc.forward(torch.from_numpy(x.astype(np.float32) / 255).permute(0, 3, 1, 2).contiguous()).numpy()
+    d = np.abs(got - ref)
+    assert d[:, :4].max() < BOX_TOL and d[:, 4].max() < SCORE_TOL
+
+
 def test_classifier_default_init_state_dict(lp):
     """the reference's own construction: torchvision random init + fc swap, default BatchNorm"""
     import torch.nn as nn
