@@ -65,10 +65,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """call at the start of the timed region: only samples after this point are reported"""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
+        self.lines = self.lines[getattr(self, "first", 0):]
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -166,7 +171,7 @@ def run_reference_arm(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -224,12 +229,16 @@ def main():
     dom_flops = 2.0 * macs[dom] * B
 
     # ---------------- device-resident throughput (value)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                     # nvidia-smi needs a few hundred ms to produce its first line
     for _ in range(args.warmup):
         pipe.run_device(fb0, CONF, IOU, MIN_AREA, frame_ids)
     barrier()
     pipe.ctx.probe_set(L.NET_DETECTOR, dom)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_spin = time.time()
+    while len(sampler.lines) == 0 and time.time() - t_spin < 3.0:
+        time.sleep(0.05)
+    sampler.mark()
     launches0 = pipe.counters.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_rois = 0
