@@ -31,7 +31,7 @@ class B200Classifier:
     def __init__(self, model_path: Optional[str], arch: str = "shufflenetv2", num_classes: int = 58,
                  input_size: int = 64, device="cpu", state_dict: Optional[dict] = None,
                  cuda_device: int = 0, max_batch: int = 256, seed: Optional[int] = None,
-                 tensor_cores: bool = True, fused: bool = True, fused_group: int = 2):
+                 tensor_cores: bool = True, fused: bool = True, fused_group: int = 1):
         # `device` is the reference's torch device string (e2e.py:354); this backend always runs on
         # cuda:`cuda_device`.  Only shufflenetv2 is implemented (ValueError like e2e.py:335 otherwise).
         if arch != "shufflenetv2":

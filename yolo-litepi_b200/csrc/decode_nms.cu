@@ -302,25 +302,31 @@ __global__ void __launch_bounds__(1024) roi_select_kernel(const float* __restric
                                                           int* __restrict__ roi_src, int* __restrict__ n_rois) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
+    __shared__ int s_first[LP_MAX_TABLE + 1];           // exclusive prefix of min(counts, max_det) over images
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_base = (img_base == 0) ? 0 : *n_rois;
+    if (tid == 0) {
+        s_base = (img_base == 0) ? 0 : *n_rois;
+        int acc = 0;
+        for (int i = 0; i < batch; ++i) { s_first[i] = acc; acc += min(counts[i], max_det); }
+        s_first[batch] = acc;
+    }
     __syncthreads();
-    const int slots = batch * max_det;
-    for (int s0 = 0; s0 < slots; s0 += 1024) {
+    const int total = s_first[batch];                   // detections actually present (not batch * max_det slots)
+    for (int s0 = 0; s0 < total; s0 += 1024) {
         const int s = s0 + tid;
         bool flag = false;
         int x1 = 0, y1 = 0, x2 = 0, y2 = 0, img = 0, k = 0;
-        if (s < slots) {
-            img = s / max_det; k = s - img * max_det;
-            if (k < min(counts[img], max_det)) {
-                const float* bx = boxes + ((long long)img * max_det + k) * 4;
-                const int w = tab.w[img], h = tab.h[img];
-                x1 = (int)bx[0]; y1 = (int)bx[1]; x2 = (int)bx[2]; y2 = (int)bx[3];   // trunc toward zero
-                x1 = min(max(x1, 0), w - 1); y1 = min(max(y1, 0), h - 1);
-                x2 = min(max(x2, x1 + 1), w); y2 = min(max(y2, y1 + 1), h);
-                const long long area = (long long)(x2 - x1) * (y2 - y1);
-                flag = (area >= (long long)min_area) && x2 > x1 && y2 > y1;
-            }
+        if (s < total) {
+            int lo = 0, hi = batch;                     // image of detection s: last i with s_first[i] <= s
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_first[mid] <= s) lo = mid; else hi = mid; }
+            img = lo; k = s - s_first[img];
+            const float* bx = boxes + ((long long)img * max_det + k) * 4;
+            const int w = tab.w[img], h = tab.h[img];
+            x1 = (int)bx[0]; y1 = (int)bx[1]; x2 = (int)bx[2]; y2 = (int)bx[3];   // trunc toward zero
+            x1 = min(max(x1, 0), w - 1); y1 = min(max(y1, 0), h - 1);
+            x2 = min(max(x2, x1 + 1), w); y2 = min(max(y2, y1 + 1), h);
+            const long long area = (long long)(x2 - x1) * (y2 - y1);
+            flag = (area >= (long long)min_area) && x2 > x1 && y2 > y1;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
         if (lane == 0) s_warp[wid] = __popc(bal);

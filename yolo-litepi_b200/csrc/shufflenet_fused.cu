@@ -2,8 +2,10 @@
 // Replaces self.model(batch) (src/vntsr/pipeline/e2e.py:393; torchvision shufflenetv2.py) for the 64x64
 // classifier input.  The layer-by-layer plan (71 launches, a few thousand pixels each) is launch- and
 // latency-bound; here every activation of a ROI lives in shared memory (<= 30 KB per ROI after the stem),
-// the folded weights (5.2 MB fp32) stream from L2 through the read-only path, and the only global traffic
-// is the 12 KB u8 crop in and C logits out.  fp32 FMA throughout (logit parity ~1e-6).
+// the folded weights (5.2 MB fp32) stream from L2 into a two-stage shared-memory ring with 1-D bulk TMA
+// (cp.async.bulk + mbarrier) issued by a dedicated producer warp that walks the same step list ahead of
+// the compute warps, and the only other global traffic is the 12 KB u8 crop in and C logits out.
+// fp32 FMA throughout (logit parity ~1e-6).
 //
 // The CTA executes a host-built step list (plan.py build_fused_classifier):
 //   front end, per ROI : conv1 3x3 s2 (+ToTensor/Normalize via a 256-entry table) -> maxpool 3x3 s2 ->
@@ -28,59 +30,103 @@ struct FStep {
     int pad0;
 };
 
-constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_THREADS = 512;            // compute threads; one more warp streams weights
+constexpr int FUSED_BLOCK = FUSED_THREADS + 32;
+constexpr int WBUF_FLOATS = 6144;             // 24 KB per weight stage, two stages
 constexpr int FUSED_MAX_STEPS = 96;
+// barrier among the compute threads only (the producer warp never joins it)
+#define CSYNC() asm volatile("bar.sync 1, %0;" ::"n"(512) : "memory")
 
-// Pointwise conv as a shared-memory GEMM: thread tile = RT rows x 4 output channels.  Weights come from
-// global memory (L2-resident, read-only path); the loop is latency-bound on them, so UNR rows of W are in
-// flight per thread (loaded into registers before the FMAs that use them) and RT is picked so that a layer
-// has >= one tile per thread.
+__device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void f_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void f_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FD_%=;\n\t"
+        "bra FW_%=;\n\t"
+        "FD_%=:\n\t}" ::"r"(f_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void f_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(f_smem_u32(bar)) : "memory");
+}
+
+// rows of W that fit one weight stage
+__device__ __forceinline__ int chunk_rows(int cin, int cout) {
+    const int cout_p = (cout + 3) & ~3;
+    const int r = WBUF_FLOATS / cout_p;
+    return r < cin ? r : cin;
+}
+
+// Pointwise conv as a shared-memory GEMM.  The activations have few rows (4..256), so the layer is bound by
+// how often a weight is re-read from shared memory: a thread owns RT rows x 4 output channels (each weight
+// float4 feeds 4*RT FMAs) and K is split over KS adjacent lanes (thread = tile * KS + ks handles the rows
+// ci == ks mod KS of every chunk) so that all 512 threads have work even when rows * cout / (4 RT) is small;
+// the KS partial sums are combined with warp shuffles.  W arrives chunk by chunk ([rows][cout_p]) in the
+// two-stage ring: wait full -> FMAs from shared memory -> every thread arrives on empty.
 template <int RT>
 __device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C, float* __restrict__ out, int out_C, int dst_cs,
-                                         int rows, int cin, int cout, const float* __restrict__ W, const float* __restrict__ bias,
-                                         int relu) {
-    constexpr int UNR = 8;
+                                         int rows, int cin, int cout, const float* __restrict__ bias, int relu, int ks_log2,
+                                         const float* __restrict__ wbuf, uint64_t* full, uint64_t* empty, uint32_t& chunk_ctr) {
     const int cout_p = (cout + 3) & ~3;
     const int ncg = cout_p >> 2, nrg = (rows + RT - 1) / RT;
-    for (int tile = threadIdx.x; tile < nrg * ncg; tile += FUSED_THREADS) {
-        const int rg = tile / ncg, cg = tile - rg * ncg;
-        const int r0 = rg * RT, c0 = cg * 4;
-        float acc[RT][4];
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    const int n_tiles = nrg * ncg;
+    const int KS = 1 << ks_log2;
+    const int ks = threadIdx.x & (KS - 1), tile = threadIdx.x >> ks_log2;
+    const bool active = tile < n_tiles;
+    const int tt = active ? tile : 0;
+    const int rg = tt / ncg, c0 = (tt - rg * ncg) * 4, r0 = rg * RT;
+    float acc[RT][4];
 #pragma unroll
-        for (int r = 0; r < RT; ++r) { acc[r][0] = b4.x; acc[r][1] = b4.y; acc[r][2] = b4.z; acc[r][3] = b4.w; }
-        const float* ip[RT];
+    for (int r = 0; r < RT; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+    int roff[RT];
 #pragma unroll
-        for (int r = 0; r < RT; ++r) ip[r] = in + (size_t)min(r0 + r, rows - 1) * in_C;
-        const float* wp = W + c0;
-        int ci = 0;
-        for (; ci + UNR <= cin; ci += UNR) {
-            float4 w[UNR];
+    for (int r = 0; r < RT; ++r) roff[r] = min(r0 + r, rows - 1) * in_C;
+    const int R = chunk_rows(cin, cout);
+    for (int k0 = 0; k0 < cin; k0 += R, ++chunk_ctr) {
+        const int nr = min(R, cin - k0);
+        const uint32_t slot = chunk_ctr & 1;
+        f_mbar_wait(&full[slot], (chunk_ctr >> 1) & 1);
+        if (active) {
+            const float* wp = wbuf + slot * WBUF_FLOATS + c0;
+            const float* ap = in + k0;
+#pragma unroll 2
+            for (int ci = ks; ci < nr; ci += KS) {
+                const float4 w = *reinterpret_cast<const float4*>(wp + ci * cout_p);
+                float a[RT];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) w[u] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(ci + u) * cout_p));
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
+                for (int r = 0; r < RT; ++r) a[r] = ap[roff[r] + ci];
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
-                    const float a = ip[r][ci + u];
-                    acc[r][0] = fmaf(a, w[u].x, acc[r][0]);
-                    acc[r][1] = fmaf(a, w[u].y, acc[r][1]);
-                    acc[r][2] = fmaf(a, w[u].z, acc[r][2]);
-                    acc[r][3] = fmaf(a, w[u].w, acc[r][3]);
+                    acc[r][0] = fmaf(a[r], w.x, acc[r][0]);
+                    acc[r][1] = fmaf(a[r], w.y, acc[r][1]);
+                    acc[r][2] = fmaf(a[r], w.z, acc[r][2]);
+                    acc[r][3] = fmaf(a[r], w.w, acc[r][3]);
                 }
             }
         }
-        for (; ci < cin; ++ci) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(wp + (size_t)ci * cout_p));
+        f_mbar_arrive(&empty[slot]);              // 512 arrivals free the stage for the producer
+    }
+    // combine the K slices (adjacent lanes)
+    for (int off = 1; off < KS; off <<= 1) {
 #pragma unroll
-            for (int r = 0; r < RT; ++r) {
-                const float a = ip[r][ci];
-                acc[r][0] = fmaf(a, w.x, acc[r][0]);
-                acc[r][1] = fmaf(a, w.y, acc[r][1]);
-                acc[r][2] = fmaf(a, w.z, acc[r][2]);
-                acc[r][3] = fmaf(a, w.w, acc[r][3]);
-            }
-        }
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][j] += __shfl_xor_sync(0xffffffffu, acc[r][j], off);
+    }
+    if (active && ks == 0) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int r = 0; r < RT; ++r) {
             if (r0 + r >= rows) break;
@@ -88,29 +134,67 @@ __device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (c0 + j < cout) {
-                    const float v = relu ? fmaxf(acc[r][j], 0.f) : acc[r][j];
-                    op[(c0 + j) * dst_cs] = v;
+                    const float v = acc[r][j] + bb[j];
+                    op[(c0 + j) * dst_cs] = relu ? fmaxf(v, 0.f) : v;
                 }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 1)
+__global__ void __launch_bounds__(FUSED_BLOCK, 1)
 shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float* __restrict__ W,
                         const FStep* __restrict__ steps, int n_front, int n_back, int G, int in_hw,
-                        float mean, float stdv, float* __restrict__ logits, int n_classes) {
+                        float mean, float stdv, float* __restrict__ logits, int n_classes, int wbuf_off,
+                        long long* dbg) {
     extern __shared__ __align__(16) float sm[];
     __shared__ FStep s_steps[FUSED_MAX_STEPS];
     __shared__ float s_norm[256];
+    __shared__ uint64_t s_full[2], s_empty[2];
     const int tid = threadIdx.x;
-    for (int i = tid; i < (n_front + n_back) * (int)(sizeof(FStep) / 4); i += FUSED_THREADS)
+    float* wbuf = sm + wbuf_off;                            // [2][WBUF_FLOATS]
+    for (int i = tid; i < (n_front + n_back) * (int)(sizeof(FStep) / 4); i += FUSED_BLOCK)
         reinterpret_cast<int*>(s_steps)[i] = reinterpret_cast<const int*>(steps)[i];
+    if (tid == 0) {
+        f_mbar_init(&s_full[0], 1); f_mbar_init(&s_full[1], 1);
+        f_mbar_init(&s_empty[0], FUSED_THREADS); f_mbar_init(&s_empty[1], FUSED_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // ToTensor + Normalize exactly as torchvision computes them: (u8 / 255 - mean) / std, IEEE divisions
     if (tid < 256) s_norm[tid] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)tid, 255.f), mean), stdv);
     __syncthreads();
     const int img_bytes = in_hw * in_hw * 3;
     const int n_groups = (n_rois + G - 1) / G;
+
+    if (tid >= FUSED_THREADS) {
+        // ================= weight producer warp: replays the step list, one bulk copy per K chunk =========
+        if (tid == FUSED_THREADS) {
+            uint32_t ctr = 0;
+            for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
+                const int ng = min(G, n_rois - group * G);
+                for (int pass = 0; pass <= ng; ++pass) {
+                    const bool back = (pass == ng);
+                    const int s_begin = back ? n_front : 0, s_end = back ? n_front + n_back : n_front;
+                    for (int si = s_begin; si < s_end; ++si) {
+                        const FStep& st = s_steps[si];
+                        if (st.op != FS_PW) continue;
+                        const int cout_p = (st.cout + 3) & ~3;
+                        const int R = chunk_rows(st.cin, st.cout);
+                        for (int k0 = 0; k0 < st.cin; k0 += R, ++ctr) {
+                            const int nr = min(R, st.cin - k0);
+                            const uint32_t slot = ctr & 1;
+                            if (ctr >= 2) f_mbar_wait(&s_empty[slot], ((ctr >> 1) - 1) & 1);
+                            const uint32_t bytes = (uint32_t)nr * cout_p * 4;
+                            f_mbar_expect_tx(&s_full[slot], bytes);
+                            f_bulk_g2s(wbuf + slot * WBUF_FLOATS, W + st.w_off + (size_t)k0 * cout_p, bytes, &s_full[slot]);
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+    uint32_t chunk_ctr = 0;
 
     for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
         const int roi0 = group * G;
@@ -124,10 +208,11 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
                 const uint4* g4 = reinterpret_cast<const uint4*>(in + (size_t)(roi0 + pass) * img_bytes);
                 uint4* s4 = reinterpret_cast<uint4*>(sm + s_steps[0].src);
                 for (int i = tid; i < img_bytes / 16; i += FUSED_THREADS) s4[i] = __ldg(g4 + i);
-                __syncthreads();
+                CSYNC();
             }
             for (int si = s_begin; si < s_end; ++si) {
                 const FStep& st = s_steps[si];
+                const long long t_step = dbg ? clock64() : 0;
                 const int rois = back ? G : 1;
                 float* dst = sm + st.dst + (back ? 0 : pass * st.dst_roi_stride);
                 const float* src = sm + st.src;
@@ -188,12 +273,20 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
                     const int rows = rois * st.H * st.W;
                     const float* ip = src + st.src_off;
                     float* op = dst + st.dst_off;
-                    // RT so that the layer has about one tile per thread (tiles = rows/RT * cout/4)
-                    const int tiles4 = ((rows + 3) / 4) * ((st.cout + 3) / 4);
-                    const int tiles2 = ((rows + 1) / 2) * ((st.cout + 3) / 4);
-                    if (tiles4 >= FUSED_THREADS - 64) pw_layer<4>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.w_off, W + st.b_off, st.relu);
-                    else if (tiles2 >= FUSED_THREADS - 64) pw_layer<2>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.w_off, W + st.b_off, st.relu);
-                    else pw_layer<1>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.w_off, W + st.b_off, st.relu);
+                    // RT = min(8, rows) rows per thread; K split over the largest power of two <= 8 that keeps
+                    // tiles * KS within the 512 compute threads (plan.py guarantees tiles <= 512)
+                    const int ncg = (st.cout + 3) >> 2;
+                    const float* bias = W + st.b_off;
+                    const int rt = rows >= 8 ? 8 : (rows >= 4 ? 4 : (rows >= 2 ? 2 : 1));
+                    const int tiles = ((rows + rt - 1) / rt) * ncg;
+                    int ksl = 0;
+                    while (ksl < 3 && (tiles << (ksl + 1)) <= FUSED_THREADS) ++ksl;
+#define PW_CALL(RT_) pw_layer<RT_>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, bias, st.relu, ksl, wbuf, s_full, s_empty, chunk_ctr)
+                    if (rt == 8) PW_CALL(8);
+                    else if (rt == 4) PW_CALL(4);
+                    else if (rt == 2) PW_CALL(2);
+                    else PW_CALL(1);
+#undef PW_CALL
                     break;
                 }
                 case FS_DW: {
@@ -209,19 +302,20 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
                     while (row < rows) {
                         const int g = row >> hw_shift, r = row & (hw_out - 1);
                         const int oy = r >> wo_shift, ox = r & (Wo - 1);
-                        float acc = __ldg(b + c);
                         const float* ip = src + (size_t)g * hw_in * st.src_C + st.src_off + c;
+                        float xv[9], wv[9];
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const int iy = oy * st.stride - 1 + ky;
-                            if (iy < 0 || iy >= st.H) continue;
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const int ix = ox * st.stride - 1 + kx;
-                                if (ix < 0 || ix >= st.W) continue;
-                                acc = fmaf(ip[(size_t)(iy * st.W + ix) * st.src_C], __ldg(w + (ky * 3 + kx) * C + c), acc);
-                            }
+                        for (int t9 = 0; t9 < 9; ++t9) {         // all loads first (clamped address, zeroed value): no branches
+                            const int iy = oy * st.stride - 1 + t9 / 3, ix = ox * st.stride - 1 + t9 % 3;
+                            const bool ok = ((unsigned)iy < (unsigned)st.H) && ((unsigned)ix < (unsigned)st.W);
+                            const int cy = min(max(iy, 0), st.H - 1), cx = min(max(ix, 0), st.W - 1);
+                            const float v = ip[(cy * st.W + cx) * st.src_C];
+                            xv[t9] = ok ? v : 0.f;
+                            wv[t9] = __ldg(w + t9 * C + c);
                         }
+                        float acc = __ldg(b + c);
+#pragma unroll
+                        for (int t9 = 0; t9 < 9; ++t9) acc = fmaf(xv[t9], wv[t9], acc);
                         dst[(size_t)row * st.dst_C + st.dst_off + c * st.dst_cs] = acc;
                         row += step_r; c += step_c;
                         if (c >= C) { c -= C; ++row; }
@@ -250,7 +344,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
                         for (int q = 0; q < hw; ++q) s += src[(size_t)(g * hw + q) * st.src_C + c];
                         dst[t] = s / (float)hw;
                     }
-                    __syncthreads();
+                    CSYNC();
                     const float* w = W + st.w_off;           // [cin][cout]
                     float* part = dst + rois * st.cin;
                     for (int j0 = 0; j0 < st.cout; j0 += 64) {
@@ -272,7 +366,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
                             }
                             part[(ks * rois + g) * 64 + (tid & 63)] = acc;
                         }
-                        __syncthreads();
+                        CSYNC();
                         for (int t = tid; t < ng * 64; t += FUSED_THREADS) {
                             const int jj = t & 63, g = t >> 6;
                             if (j0 + jj < st.cout) {
@@ -281,12 +375,13 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
                                 logits[(size_t)(roi0 + g) * n_classes + j0 + jj] = acc;
                             }
                         }
-                        __syncthreads();
+                        CSYNC();
                     }
                     break;
                 }
                 }
-                __syncthreads();
+                CSYNC();
+                if (dbg && blockIdx.x == 0 && tid == 0) dbg[si] += clock64() - t_step;
             }
         }
     }
@@ -297,6 +392,7 @@ struct lp_fused_cls {
     const float* weights = nullptr;
     int n_front = 0, n_back = 0, G = 0, in_hw = 0, n_classes = 0;
     size_t smem_bytes = 0;
+    int wbuf_off = 0;
     float mean = 0.f, stdv = 1.f;
     bool loaded = false;
 };
@@ -310,7 +406,12 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
     LP_CHECK(ctx->fused_slot >= 0 && ctx->fused_slot < 16, "lp_fused_classifier_load: too many contexts");
     lp_fused_cls& f = g_fused[ctx->fused_slot];
     f.steps_dev = (const FStep*)steps_dev; f.weights = weights; f.n_front = n_front; f.n_back = n_back;
-    f.G = group; f.in_hw = in_hw; f.n_classes = n_classes; f.smem_bytes = smem_bytes; f.mean = mean; f.stdv = stdv;
+    f.G = group; f.in_hw = in_hw; f.n_classes = n_classes; f.mean = mean; f.stdv = stdv;
+    // the host-built map covers the activations; the two weight stages are appended here
+    f.wbuf_off = (int)((smem_bytes + 15) / 16 * 4);
+    f.smem_bytes = (size_t)f.wbuf_off * 4 + 2 * WBUF_FLOATS * 4;
+    smem_bytes = f.smem_bytes;
+    LP_CHECK(smem_bytes <= 218 * 1024, "lp_fused_classifier_load: group %d needs %zu B shared memory", group, smem_bytes);
     LP_CUDA(cudaFuncSetAttribute(shufflenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     f.loaded = true;
     return 0;
@@ -322,8 +423,8 @@ int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cuda
     const lp_fused_cls& f = g_fused[ctx->fused_slot];
     const int groups = (n + f.G - 1) / f.G;
     const int grid = groups < ctx->sm_count ? groups : ctx->sm_count;
-    shufflenet_fused_kernel<<<grid, FUSED_THREADS, f.smem_bytes, st>>>(in, n, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
-                                                                       f.in_hw, f.mean, f.stdv, logits, f.n_classes);
+    shufflenet_fused_kernel<<<grid, FUSED_BLOCK, f.smem_bytes, st>>>(in, n, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
+                                                                     f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, ctx->tc_dbg);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(e)); return -2; }
