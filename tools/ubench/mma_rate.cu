@@ -36,6 +36,22 @@ __global__ void __launch_bounds__(128, 1) k(int N, uint32_t sbo_a, uint32_t lbo_
         const uint32_t d0 = tb, d1 = tb + (nacc > 1 ? N : 0);
         long long t0 = clock64();
 #define MMA(D, A, B) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(D), "l"(A), "l"(B), "r"(idesc), "r"(1) : "memory")
+        if (distinct_desc == 2) {
+            // fresh operands for every MMA pair, like the conv kernel: A advances 2*LBO per K-step over a 47 KB
+            // patch (two planes), B advances through 64 KB of weights
+            const uint32_t a_step = (2 * lbo_a) >> 4, plane = (8 * lbo_a) >> 4, b_step = (2u * N * 32) >> 4;
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | (8u << 24);
+            const uint64_t dbb = umma_desc(b0, (uint32_t)N * 32, 128, 0);
+            for (int i = 0; i < iters; i += 8) {
+                uint32_t ao = ((uint32_t)(i / 8) % 9) * 1, bo = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    MMA(d0, da0 + ao, dbb + bo);   /* N here is idesc's N; uses idesc (N) for simplicity */
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d0), "l"(da0 + ao + plane), "l"(dbb + bo), "r"(idesc2), "r"(1) : "memory");
+                    ao += a_step; bo += b_step;
+                }
+            }
+        } else
         for (int i = 0; i < iters; i += 8) {
             if (distinct_desc) { MMA(d0, da0, db0); MMA(d1, da1, db0); MMA(d0, da0, db1); MMA(d1, da1, db1); MMA(d0, da1, db0); MMA(d1, da0, db1); MMA(d0, da1, db1); MMA(d1, da0, db0); }
             else { MMA(d0, da0, db0); MMA(d1, da0, db0); MMA(d0, da0, db0); MMA(d1, da0, db0); MMA(d0, da0, db0); MMA(d1, da0, db0); MMA(d0, da0, db0); MMA(d1, da0, db0); }
@@ -58,7 +74,8 @@ int main() {
     for (int N : {16, 32, 64, 128, 256})
         for (uint32_t sbo : {128u, 160u})
             for (int nacc : {1, 2})
-                for (int dd : {0, 1}) {
+                for (int dd : {0, 1, 2}) {
+                    if (dd == 2 && (layout != 0 || N > 128 || nacc != 1)) continue;
                     if (layout == 2 && sbo != 128) continue;
                     if (nacc * N > 512) continue;
                     const uint32_t lbo = layout ? 16 : 2896, sb = layout ? 1024 : sbo;

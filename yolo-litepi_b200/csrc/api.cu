@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
 
@@ -36,6 +37,7 @@ extern "C" int lp_create(lp_ctx** out, int device) {
     static int next_slot = 0;
     c->fused_slot = next_slot++ % 16;
     c->device = device;
+    { const char* e = getenv("LP_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
     c->sm_count = prop.multiProcessorCount;
     *out = c;
     return 0;

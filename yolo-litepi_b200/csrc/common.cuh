@@ -63,6 +63,7 @@ struct lp_ctx {
     int probe_n = 0;
     int fused_slot = -1;             // index into the fused-classifier table (shufflenet_fused.cu)
     int use_fused = 1;
+    int use_pdl = 1;                 // programmatic dependent launch between tensor-core conv kernels (env LP_NO_PDL=1 disables)
     long long* tc_dbg = nullptr;     // device buffer (16 x int64) for conv_tc role timing; debugging only
 };
 #define LP_PROBE_RING 512

@@ -199,6 +199,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hw_in = p.H * p.W, hw_out = p.Ho * p.Wo;
 
+    // Programmatic dependent launch: the next kernel of the plan may start its prologue (barriers, TMEM,
+    // weight stream) while this grid drains; every access to activations happens after griddepcontrol.wait.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < MAX_PST; ++s) { mbar_init(&patch_full[s], LOADER_THREADS); mbar_init(&patch_empty[s], 1); }
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
             asm volatile("bar.sync 1, %0;" ::"n"(LOADER_THREADS) : "memory");      // loaders only
         }
+        asm volatile("griddepcontrol.wait;" ::: "memory");      // activations of the previous layer are complete and visible
         // Up to `depth` tiles are in flight per thread (one cp.async group each): a tile costs a full
         // L2/HBM round trip, so the loader must not wait for tile i before issuing tile i+1.
         const int depth = p.patch_stages - 1 < 4 ? p.patch_stages - 1 : 4;
@@ -442,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         const uint32_t epi_plane = (uint32_t)TILE_M * p.epi_pitch;
         long long* row_base = reinterpret_cast<long long*>(epi + (size_t)n_planes * epi_plane);
         const bool staged = p.epi_bytes > 0;
+        asm volatile("griddepcontrol.wait;" ::: "memory");      // before any residual read / output write
         int it = 0;
         long long e_wait = 0, e_total0 = TCLK(), e_p1 = 0, e_bar = 0, e_p2 = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -736,8 +742,14 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         attr_set = true;
     }
     const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         lp_set_error("conv_tc launch failed: %s (smem %zu)", cudaGetErrorString(e), smem);
         return -2;
