@@ -143,6 +143,7 @@ extern "C" int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int 
     }
     P.workspace_bytes = need;
     P.loaded = true;
+    if (net == LP_NET_DETECTOR) return lp_assign_small_slots(P, 0);     // classifier: the fused kernel is the product path
     return 0;
 }
 

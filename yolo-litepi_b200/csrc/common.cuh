@@ -49,6 +49,7 @@ struct lp_net_plan {
     int max_batch = 0;
     size_t workspace_bytes = 0;     // max over bufs of offset + max_batch * image_bytes
     bool loaded = false;
+    std::vector<int> small_slot;    // per op: constant-memory slot of the small-channel conv path, or -1
 };
 
 struct lp_ctx {
@@ -83,5 +84,6 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
 int lp_launch_detect_tail(lp_ctx* ctx, const float* head_raw, int batch, int head_c, float* out0, cudaStream_t st);
 
 // tensor-core path (conv_tc.cu); returns 1 if it handled the op, 0 if not applicable, <0 on error
+int lp_assign_small_slots(lp_net_plan& net, cudaStream_t st);
 int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cudaStream_t st);
 int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st);

@@ -313,6 +313,117 @@ __global__ void __launch_bounds__(CONV_THREADS) stem_u8_kernel(ConvParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small-channel convs (Cin 3 / 8 / 24: the first five detector layers).  They cannot feed a tensor core
+// and the generic kernel is bound by its shared-memory weight reads (one LDS per 4 FMAs), so here the
+// weights live in CONSTANT memory: an FFMA takes its weight operand straight from the constant bank, the
+// only shared-memory traffic is one input read per Cout FMAs.  One thread = one output pixel x all Cout.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_SLOTS = 6, SMALL_W_FLOATS = 2048, SMALL_SLOT_FLOATS = SMALL_W_FLOATS + 32;
+__constant__ float c_small[SMALL_SLOTS][SMALL_SLOT_FLOATS];      // [tap][cin][cout] then bias[cout] at SMALL_W_FLOATS
+
+template <int KS, int STRIDE, int CIN, int COUT, bool U8IN>
+__global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, int slot) {
+    constexpr int PH = (KS == 1) ? 1 : (TILE_H - 1) * STRIDE + KS;
+    constexpr int PW = (KS == 1) ? CONV_THREADS : (TILE_W - 1) * STRIDE + KS;
+    constexpr int CINP = U8IN ? CIN : ((CIN + 7) / 8) * 8;
+    __shared__ float s_patch[CINP][PH][PW + 1];
+    const int tid = threadIdx.x;
+    int img, oy, ox, ty = 0, tx = tid, tile_y0 = 0, tile_x0 = 0;
+    bool valid;
+    if (KS == 1) {
+        const long long m = (long long)blockIdx.x * CONV_THREADS + tid;
+        const long long total = (long long)p.n_img * p.Ho * p.Wo;
+        valid = m < total;
+        const long long mm = valid ? m : 0;
+        img = (int)(mm / ((long long)p.Ho * p.Wo));
+        const int r = (int)(mm - (long long)img * p.Ho * p.Wo);
+        oy = r / p.Wo; ox = r - oy * p.Wo;
+        float v[CINP];
+#pragma unroll
+        for (int i = 0; i < CINP; ++i) v[i] = 0.f;
+        if (valid) {
+            const long long idx = (long long)img * p.in.img + ((long long)oy * p.W + ox) * p.in.C + p.in.coff;
+#pragma unroll
+            for (int c8 = 0; c8 < CINP; c8 += 8) ld8(p.in, idx + c8, v + c8);
+        }
+#pragma unroll
+        for (int i = 0; i < CIN; ++i) s_patch[i][0][tid] = v[i];
+    } else {
+        const int tiles_x = (p.Wo + TILE_W - 1) / TILE_W;
+        img = blockIdx.z;
+        tile_y0 = (blockIdx.x / tiles_x) * TILE_H; tile_x0 = (blockIdx.x % tiles_x) * TILE_W;
+        ty = tid / TILE_W; tx = tid % TILE_W;
+        oy = tile_y0 + ty; ox = tile_x0 + tx;
+        valid = (oy < p.Ho && ox < p.Wo);
+        const int iy0 = tile_y0 * STRIDE - KS / 2, ix0 = tile_x0 * STRIDE - KS / 2;
+        for (int e = tid; e < PH * PW; e += CONV_THREADS) {
+            const int py = e / PW, px = e - py * PW;
+            const int iy = iy0 + py, ix = ix0 + px;
+            const bool in = (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W);
+            if (U8IN) {
+                float v[3] = {0.f, 0.f, 0.f};
+                if (in) {
+                    const uint8_t* q = (const uint8_t*)p.in.base + (long long)img * p.in.img + ((long long)iy * p.W + ix) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float x = __fdiv_rn((float)q[c], 255.f);
+                        if (p.in_scale_std != 1.f || p.in_scale_mean != 0.f) x = __fdiv_rn(__fsub_rn(x, p.in_scale_mean), p.in_scale_std);
+                        v[c] = x;
+                    }
+                }
+                s_patch[0][py][px] = v[0]; s_patch[1][py][px] = v[1]; s_patch[2][py][px] = v[2];
+            } else {
+                float v[CINP];
+#pragma unroll
+                for (int i = 0; i < CINP; ++i) v[i] = 0.f;
+                if (in) {
+                    const long long idx = (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff;
+#pragma unroll
+                    for (int c8 = 0; c8 < CINP; c8 += 8) ld8(p.in, idx + c8, v + c8);
+                }
+#pragma unroll
+                for (int i = 0; i < CIN; ++i) s_patch[i][py][px] = v[i];
+            }
+        }
+    }
+    __syncthreads();
+    if (!valid) return;
+    const float* cw = c_small[slot];
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = cw[SMALL_W_FLOATS + co];
+#pragma unroll
+    for (int t = 0; t < KS * KS; ++t) {
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float a = (KS == 1) ? s_patch[ci][0][tid] : s_patch[ci][ty * STRIDE + t / KS][tx * STRIDE + t % KS];
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(a, cw[(t * CIN + ci) * COUT + co], acc[co]);
+        }
+    }
+    const long long opix = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff;
+#pragma unroll
+    for (int g = 0; g < COUT / 8; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = act_apply(acc[g * 8 + i], p.act);
+        st8(p.out, opix + g * 8, v);
+    }
+}
+
+// returns true if a specialisation exists for this shape (v1 widths 8/16, v2 widths 16/24 stem)
+template <typename F> static bool small_dispatch(int ks, int stride, int cin, int cout, bool u8, F&& f) {
+#define LP_SMALL(K, S, CI, CO, U) if (ks == K && stride == S && cin == CI && cout == CO && u8 == U) { f(conv_small_kernel<K, S, CI, CO, U>); return true; }
+    LP_SMALL(3, 2, 3, 8, true)
+    LP_SMALL(3, 2, 3, 16, true)
+    LP_SMALL(3, 2, 8, 16, false)
+    LP_SMALL(3, 1, 8, 8, false)
+    LP_SMALL(1, 1, 24, 16, false)
+#undef LP_SMALL
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Memory-bound glue: depthwise 3x3, max pool, nearest x2 upsample, channel-slice copy, mean+FC.
 // One thread per (pixel, channel); channels fastest so warps read/write contiguous NHWC runs.
 // ---------------------------------------------------------------------------------------------
@@ -460,6 +571,30 @@ __global__ void mean_fc_kernel(ConvParams p, float* __restrict__ logits) {
 // ---------------------------------------------------------------------------------------------
 // Plan executor
 // ---------------------------------------------------------------------------------------------
+// Assign constant-memory slots to the small-channel convs of a plan and upload their weights (device ->
+// constant).  Slots are a process-wide resource (one module); plans that come late fall back to the
+// generic kernel.
+int lp_assign_small_slots(lp_net_plan& net, cudaStream_t st) {
+    static int next_slot = 0;
+    net.small_slot.assign(net.ops.size(), -1);
+    for (size_t i = 0; i < net.ops.size(); ++i) {
+        const lp_op_desc& op = net.ops[i];
+        if (op.kind != LP_OP_STEM_U8 && op.kind != LP_OP_CONV) continue;
+        const int nw = op.ksize * op.ksize * op.cin * op.cout;
+        if (nw > SMALL_W_FLOATS || op.cout > 32 || next_slot >= SMALL_SLOTS) continue;
+        bool have = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [](auto) {});
+        if (!have) continue;
+        const int slot = next_slot++;
+        LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.w_off, (size_t)nw * 4, (size_t)slot * SMALL_SLOT_FLOATS * 4,
+                                        cudaMemcpyDeviceToDevice, st));
+        LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.b_off, (size_t)op.cout * 4,
+                                        ((size_t)slot * SMALL_SLOT_FLOATS + SMALL_W_FLOATS) * 4, cudaMemcpyDeviceToDevice, st));
+        net.small_slot[i] = slot;
+    }
+    LP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 static TensorRef make_ref(const lp_net_plan& net, int buf, int coff, uint8_t* ws, int row_off) {
     TensorRef t{};
     if (buf < 0) { t.base = nullptr; return t; }
@@ -533,6 +668,18 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                 LP_CHECK(ob.h == p.Ho && ob.w == p.Wo, "op %zu: output buffer %dx%d != computed %dx%d", oi, ob.h, ob.w, p.Ho, p.Wo);
         }
         const long long total = (long long)batch * p.Ho * p.Wo * p.cout;
+        if ((op.kind == LP_OP_STEM_U8 || op.kind == LP_OP_CONV) && net.small_slot.size() > oi && net.small_slot[oi] >= 0 &&
+            p.res.base == nullptr && p.seg_len == 0 && p.out_cstride == 1 && p.out.fmt == LP_FMT_SPLIT16 &&
+            (op.kind == LP_OP_STEM_U8 || p.in.fmt == LP_FMT_SPLIT16) && p.in.coff % 8 == 0 && p.out.coff % 8 == 0) {
+            const int slot = net.small_slot[oi];
+            const bool ran = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [&](auto kern) {
+                dim3 grid;
+                if (op.ksize == 1) grid = dim3((unsigned)(((long long)batch * p.Ho * p.Wo + CONV_THREADS - 1) / CONV_THREADS), 1, 1);
+                else grid = dim3(((p.Wo + TILE_W - 1) / TILE_W) * ((p.Ho + TILE_H - 1) / TILE_H), 1, batch);
+                kern<<<grid, CONV_THREADS, 0, st>>>(p, slot);
+            });
+            if (ran) { LP_LAUNCH_OK(ctx); continue; }
+        }
         switch (op.kind) {
         case LP_OP_STEM_U8: {
             LP_CHECK(op.ksize == 3 && op.stride == 2 && op.cout <= 32, "stem: unsupported shape");
