@@ -14,6 +14,7 @@
 //                        GEMM rows so each weight is fetched once per group.
 // channel_shuffle is the store pattern of the producers (dst channel = off + j * 2), chunk is a view.
 #include "common.cuh"
+#include <stdlib.h>
 
 enum { FS_CONV1 = 0, FS_MAXPOOL = 1, FS_PW = 2, FS_DW = 3, FS_COPY = 4, FS_MEANFC = 5 };
 
@@ -59,6 +60,31 @@ __device__ __forceinline__ void f_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void f_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f_smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(f_smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t f_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void f_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same-named mbarrier of CTA `rank` of the cluster
+__device__ __forceinline__ void f_mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(f_smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "CW_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra CD_%=;\n\t"
+        "bra CW_%=;\n\t"
+        "CD_%=:\n\t}" ::"r"(f_smem_u32(bar)), "r"(parity) : "memory");
+}
+// one L2 read, delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void f_bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(f_smem_u32(dst)), "l"(src), "r"(bytes), "r"(f_smem_u32(bar)), "h"(mask) : "memory");
 }
 
 // rows of W that fit one weight stage
@@ -146,11 +172,11 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 1)
 shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float* __restrict__ W,
                         const FStep* __restrict__ steps, int n_front, int n_back, int G, int in_hw,
                         float mean, float stdv, float* __restrict__ logits, int n_classes, int wbuf_off,
-                        long long* dbg) {
+                        long long* dbg, int cs) {
     extern __shared__ __align__(16) float sm[];
     __shared__ FStep s_steps[FUSED_MAX_STEPS];
     __shared__ float s_norm[256];
-    __shared__ uint64_t s_full[2], s_empty[2];
+    __shared__ uint64_t s_full[2], s_empty[2], s_cready[2];   // weights landed / consumed (local) / every CTA armed (leader)
     const int tid = threadIdx.x;
     float* wbuf = sm + wbuf_off;                            // [2][WBUF_FLOATS]
     for (int i = tid; i < (n_front + n_back) * (int)(sizeof(FStep) / 4); i += FUSED_BLOCK)
@@ -158,22 +184,32 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
     if (tid == 0) {
         f_mbar_init(&s_full[0], 1); f_mbar_init(&s_full[1], 1);
         f_mbar_init(&s_empty[0], FUSED_THREADS); f_mbar_init(&s_empty[1], FUSED_THREADS);
+        f_mbar_init(&s_cready[0], cs); f_mbar_init(&s_cready[1], cs);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ToTensor + Normalize exactly as torchvision computes them: (u8 / 255 - mean) / std, IEEE divisions
     if (tid < 256) s_norm[tid] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)tid, 255.f), mean), stdv);
     __syncthreads();
+    f_cluster_sync();                                        // every CTA's barriers exist before any remote arrive / multicast
     const int img_bytes = in_hw * in_hw * 3;
     const int n_groups = (n_rois + G - 1) / G;
+    // every CTA of a cluster runs the same number of iterations (the weight stream is shared); CTAs whose
+    // group index is past the end compute on stale data and write nothing
+    const int n_iters = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (tid >= FUSED_THREADS) {
         // ================= weight producer warp: replays the step list, one bulk copy per K chunk =========
+        // Cluster protocol per chunk: every CTA's producer waits until its own consumers released the stage,
+        // arms its local `full` barrier with the byte count and tells the leader (remote arrive on cready);
+        // the leader waits for all CTAs and issues ONE multicast bulk copy that lands in every CTA's stage
+        // and completes every CTA's `full` barrier.  L2 weight traffic per ROI drops by the cluster size.
         if (tid == FUSED_THREADS) {
+            const uint32_t rank = f_cluster_rank();
+            const uint16_t mask = (uint16_t)((1u << cs) - 1u);
             uint32_t ctr = 0;
-            for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
-                const int ng = min(G, n_rois - group * G);
-                for (int pass = 0; pass <= ng; ++pass) {
-                    const bool back = (pass == ng);
+            for (int iter = 0; iter < n_iters; ++iter) {
+                for (int pass = 0; pass <= G; ++pass) {
+                    const bool back = (pass == G);
                     const int s_begin = back ? n_front : 0, s_end = back ? n_front + n_back : n_front;
                     for (int si = s_begin; si < s_end; ++si) {
                         const FStep& st = s_steps[si];
@@ -186,24 +222,28 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
                             if (ctr >= 2) f_mbar_wait(&s_empty[slot], ((ctr >> 1) - 1) & 1);
                             const uint32_t bytes = (uint32_t)nr * cout_p * 4;
                             f_mbar_expect_tx(&s_full[slot], bytes);
-                            f_bulk_g2s(wbuf + slot * WBUF_FLOATS, W + st.w_off + (size_t)k0 * cout_p, bytes, &s_full[slot]);
+                            f_mbar_arrive_remote(&s_cready[slot], 0);
+                            if (rank == 0) {
+                                f_mbar_wait_cluster(&s_cready[slot], (ctr >> 1) & 1);
+                                f_bulk_g2s_multicast(wbuf + slot * WBUF_FLOATS, W + st.w_off + (size_t)k0 * cout_p, bytes, &s_full[slot], mask);
+                            }
                         }
                     }
                 }
             }
         }
-        return;
-    }
+    } else {
     uint32_t chunk_ctr = 0;
 
-    for (int group = blockIdx.x; group < n_groups; group += gridDim.x) {
+    for (int iter = 0; iter < n_iters; ++iter) {
+        const int group = blockIdx.x + iter * gridDim.x;
         const int roi0 = group * G;
-        const int ng = min(G, n_rois - roi0);
-        for (int pass = 0; pass <= ng; ++pass) {
-            // pass < ng: front end of ROI `pass`; pass == ng: back end of the whole group
-            const bool back = (pass == ng);
+        const int ng = max(0, min(G, n_rois - roi0));       // real ROIs of this group (0 for a padding group)
+        for (int pass = 0; pass <= G; ++pass) {
+            // pass < G: front end of ROI `pass`; pass == G: back end of the whole group
+            const bool back = (pass == G);
             const int s_begin = back ? n_front : 0, s_end = back ? n_front + n_back : n_front;
-            if (!back) {
+            if (!back && pass < ng) {
                 // stage the u8 crop (16-B copies); the CONV1 step's src is its float offset
                 const uint4* g4 = reinterpret_cast<const uint4*>(in + (size_t)(roi0 + pass) * img_bytes);
                 uint4* s4 = reinterpret_cast<uint4*>(sm + s_steps[0].src);
@@ -385,6 +425,8 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
             }
         }
     }
+    }   // compute threads
+    f_cluster_sync();        // no CTA leaves while a peer may still multicast into it or arrive on its barriers
 }
 
 struct lp_fused_cls {
@@ -393,6 +435,8 @@ struct lp_fused_cls {
     int n_front = 0, n_back = 0, G = 0, in_hw = 0, n_classes = 0;
     size_t smem_bytes = 0;
     int wbuf_off = 0;
+    int cluster = 1;            // CTAs sharing one multicast weight stream (env LP_CLS_CLUSTER; measured: 2 = no gain, the
+                                // stream is bound by bytes in flight per SM, not by L2; 4+ halves the resident CTAs)
     float mean = 0.f, stdv = 1.f;
     bool loaded = false;
 };
@@ -413,6 +457,7 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
     smem_bytes = f.smem_bytes;
     LP_CHECK(smem_bytes <= 218 * 1024, "lp_fused_classifier_load: group %d needs %zu B shared memory", group, smem_bytes);
     LP_CUDA(cudaFuncSetAttribute(shufflenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    { const char* e = getenv("LP_CLS_CLUSTER"); f.cluster = e ? atoi(e) : 1; if (f.cluster < 1 || f.cluster > 8) f.cluster = 1; }
     f.loaded = true;
     return 0;
 }
@@ -422,9 +467,19 @@ int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cuda
     if (ctx->fused_slot < 0 || ctx->fused_slot >= 16 || !g_fused[ctx->fused_slot].loaded || !ctx->use_fused) return 0;
     const lp_fused_cls& f = g_fused[ctx->fused_slot];
     const int groups = (n + f.G - 1) / f.G;
-    const int grid = groups < ctx->sm_count ? groups : ctx->sm_count;
-    shufflenet_fused_kernel<<<grid, FUSED_BLOCK, f.smem_bytes, st>>>(in, n, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
-                                                                     f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, ctx->tc_dbg);
+    const int cs = f.cluster;
+    int grid = groups < ctx->sm_count ? groups : ctx->sm_count;
+    grid = (grid + cs - 1) / cs * cs;
+    if (grid > ctx->sm_count) grid = ctx->sm_count / cs * cs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FUSED_BLOCK); cfg.dynamicSmemBytes = f.smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
+                                        f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, ctx->tc_dbg, cs);
+    if (le != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(le)); return -2; }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(e)); return -2; }
