@@ -65,7 +65,22 @@ __global__ void __launch_bounds__(128, 1) k(int N, uint32_t sbo_a, uint32_t lbo_
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512) : "memory");
 }
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1) {
+        // LBO sweep of the conv pattern (dd = 2): mma_rate sweep
+        long long* d; cudaMalloc(&d, 8);
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        printf("N lbo16 (mod 8) cycles/mma\n");
+        for (int N : {32, 64, 128})
+            for (uint32_t l16 : {176u, 177u, 178u, 179u, 180u, 181u, 182u, 183u, 184u, 185u})
+                for (uint32_t sbo : {128u, 160u}) {
+                    k<<<148, 128, 160 * 1024>>>(N, sbo, l16 * 16, 2000, 1, 2, 0, d);
+                    cudaDeviceSynchronize();
+                    long long c; cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+                    printf("%3d %3u %u sbo %u %8.1f\n", N, l16, l16 % 8, sbo, (double)c / 2000);
+                }
+        return 0;
+    }
     long long* d; cudaMalloc(&d, 8);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 2000;

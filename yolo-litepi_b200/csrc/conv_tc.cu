@@ -56,7 +56,9 @@ struct TcParams {
     int slots, slots_p;        // patch pixels, padded count (LBO_A = slots_p * 16 B)
     int pitch;                 // patch row pitch in pixels (SBO_A = pitch * 16 B); 1x1: 8
     int phase_slots;           // stride 2: slots per parity phase
-    int kb_ch, n_cb, n_kb;     // channels per K-block, channel blocks, total K-blocks (taps * n_cb)
+    int kb_ch, n_cb, n_kb;     // channels per K unit, channel blocks per tap, weight blocks per tile
+    int tap_off[9];            // A start offset of each tap inside a patch, in 16-B slots (constant-bank operands of the issue loop)
+    int n_units, upb, unit_bytes;   // K units (tap x channel block) per tile, units per weight block, bytes per unit
     int w_stages, stage_bytes, resident;
     int patch_stages, acc_stages;
     int n_mma, mtab_bytes;     // MMA issue table: one uint2 per tcgen05.mma of a tile
@@ -160,7 +162,10 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     return v;
 }
 
-#define TCLK() (p.dbg ? clock64() : 0ll)
+// role timing exists only in the DBG instantiation: on the single-warp MMA issue path every instruction
+// costs ~9 cycles, so the production kernel carries no clock reads, flag tests or 64-bit counters
+#define TCLK() (DBG ? clock64() : 0ll)
+#define DFLAG(bit) (DBG && (p.dbg_flags & (bit)))
 struct TileCoord { int img, oy0, ox0; long long pix0; };
 
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
@@ -178,6 +183,7 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
 }
 
 // smem carve-up: [barriers 512 B][patch ring][weight stages]
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);        // [MAX_WST]
@@ -218,7 +224,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= W_LOADER0) {
+    const bool pure = DFLAG(8);      // debugging: MMA warp alone, no barriers (measures the raw MMA rate)
+    if (pure && warp != W_MMA) {
+    } else if (warp >= W_LOADER0) {
         // ================= patch loaders (256 threads) =================
         // The loader's instruction stream is on the critical path of the small-channel layers, so the
         // tile-independent geometry of every 16-B item is tabulated once; per tile an item costs ~15
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             t_wait_empty += t1 - t0;
             const TileCoord tc = tile_coord(p, tile);
             const uint32_t dst0 = smem_u32(patch0 + (size_t)ps * patch_bytes);
-            if (p.dbg_flags & 1) {
+            if (DFLAG(1)) {
             } else if (p.ksize == 1) {
                 // images are contiguous (host checks in_img == H*W*C): flattened pixel index addresses directly
                 const __half* base = in_c + tc.pix0 * p.in_C;
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 t_wait_cp += TCLK() - t2;
             }
         }
-        if (p.dbg && blockIdx.x == 0 && lt == 0) { p.dbg[0] = t_wait_empty; p.dbg[1] = t_issue; p.dbg[2] = t_wait_cp; }
+        if (DBG && p.dbg && blockIdx.x == 0 && lt == 0) { p.dbg[0] = t_wait_empty; p.dbg[1] = t_issue; p.dbg[2] = t_wait_cp; }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (; arrived < issued; ++arrived) mbar_arrive(&patch_full[arrived % p.patch_stages]);
@@ -325,9 +333,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 for (int kb = 0; kb < p.n_kb; ++kb, ++g) {
                     const int s = g % p.w_stages;
                     if (g >= p.w_stages) mbar_wait(&w_empty[s], ((g / p.w_stages) - 1) & 1);
-                    if ((p.dbg_flags & 4) && g >= p.w_stages) { mbar_arrive(&w_full[s]); continue; }
-                    mbar_expect_tx(&w_full[s], (uint32_t)p.stage_bytes);
-                    bulk_g2s(wst + (size_t)s * p.stage_bytes, p.wtc + (size_t)kb * p.stage_bytes, (uint32_t)p.stage_bytes, &w_full[s]);
+                    if (DFLAG(4) && g >= p.w_stages) { mbar_arrive(&w_full[s]); continue; }
+                    const int units = min(p.upb, p.n_units - kb * p.upb);        // the last block of a tile may be short
+                    const uint32_t bytes = (uint32_t)units * p.unit_bytes;
+                    mbar_expect_tx(&w_full[s], bytes);
+                    bulk_g2s(wst + (size_t)s * p.stage_bytes, p.wtc + (size_t)kb * p.stage_bytes, bytes, &w_full[s]);
                 }
             }
         }
@@ -350,83 +360,96 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             const uint32_t b016 = (uint32_t)db_base + (smem_u32(wst) >> 4);
             const uint32_t plane16 = plane_bytes >> 4;
             const uint32_t a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
-            const uint32_t b_wrap16 = (uint32_t)p.w_stages * ((uint32_t)p.stage_bytes >> 4);
             const uint32_t patch016 = da_lo0 + (smem_u32(patch0) >> 4), patch_stride16 = patch_bytes >> 4;
             const int ksteps = p.kb_ch >> 4, ktot = p.cin >> 4, taps = p.ksize * p.ksize;
             const uint32_t leader = elect_one() ? 1u : 0u;
             (void)mtab;
             int it = 0;
-            uint32_t fill = 0;                              // streaming: K-blocks consumed so far (all tiles)
+            // ring positions advance incrementally: a division by a runtime stage count costs ~20 dependent
+            // instructions on this warp, more than the MMAs of a whole K unit
+            uint32_t ps = 0, ps_phase = 0, as = 0, as_phase = 0, st = 0, st_phase = 0;
             long long m_wait_acc = 0, m_wait_patch = 0, m_wait_w = 0, m_total0 = TCLK();
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                const int ps = it % p.patch_stages, as = it % p.acc_stages;
                 long long t0 = TCLK();
-                if (it >= p.acc_stages) mbar_wait(&acc_empty[as], ((it / p.acc_stages) - 1) & 1);
+                if (!pure && it >= p.acc_stages) mbar_wait(&acc_empty[as], as_phase ^ 1);
                 long long t1 = TCLK();
-                mbar_wait(&patch_full[ps], (it / p.patch_stages) & 1);
+                if (!pure) mbar_wait(&patch_full[ps], ps_phase);
                 long long t2 = TCLK();
                 m_wait_acc += t1 - t0; m_wait_patch += t2 - t1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t patch16 = patch016 + (uint32_t)ps * patch_stride16;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
                 uint32_t acc = 0;
+                // Taps are unrolled so that each tap offset is a constant-bank operand; per tap the warp spends one
+                // add, per K-step two MMAs and three adds.
                 if (p.resident) {
-                    if (it == 0) {                          // the whole layer lands once
+                    if (it == 0 && !pure) {                 // the whole layer lands once
                         for (int kb = 0; kb < p.n_kb; ++kb) mbar_wait(&w_full[kb], 0);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     uint32_t b16 = b016;
-                    uint32_t trow = 0;                      // tap row offset (ky * pitch) / phase offset
-                    for (int tap = 0; tap < taps; ++tap) {
-                        uint32_t a16 = patch16;
-                        if (p.ksize == 3) {
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            a16 += (p.stride == 1) ? (uint32_t)(ky * p.pitch + kx)
-                                                   : (uint32_t)(((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1));
-                        }
-                        for (int kk = 0; kk < ktot; ++kk) {
-                            umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);           // Ahi x [Bhi|Blo]
-                            umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);   // Alo x Bhi
-                            acc = 1;
-                            a16 += a_step16;
-                            b16 += b_step16;
-                        }
-                    }
-                    (void)trow;
-                } else {
-                    uint32_t b16 = b016 + (fill % (uint32_t)p.w_stages) * ((uint32_t)p.stage_bytes >> 4);
-                    for (int tap = 0; tap < taps; ++tap) {
-                        uint32_t a16 = patch16;
-                        if (p.ksize == 3) {
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            a16 += (p.stride == 1) ? (uint32_t)(ky * p.pitch + kx)
-                                                   : (uint32_t)(((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1));
-                        }
-                        for (int cb = 0; cb < p.n_cb; ++cb, ++fill) {
-                            const uint32_t st = fill % (uint32_t)p.w_stages;
-                            long long t3 = TCLK();
-                            mbar_wait(&w_full[st], (fill / (uint32_t)p.w_stages) & 1);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            m_wait_w += TCLK() - t3;
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);
-                                umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (tap < taps) {
+                            uint32_t a16 = patch16 + (uint32_t)p.tap_off[tap];
+                            for (int kk = 0; kk < ktot; ++kk) {
+                                umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);           // Ahi x [Bhi|Blo]
+                                umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);   // Alo x Bhi
                                 acc = 1;
                                 a16 += a_step16;
                                 b16 += b_step16;
                             }
-                            if (leader) umma_commit(&w_empty[st]);      // frees the weight stage once these MMAs retire
-                            if (st + 1 == (uint32_t)p.w_stages) b16 -= b_wrap16;
+                        }
+                    }
+                } else {
+                    // weight blocks of `upb` K units (tap x channel block) stream through the ring: one barrier
+                    // wait and one commit per BLOCK, B advances linearly inside a block
+                    const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+                    uint32_t b16 = 0;
+                    int u_in_blk = 0, units_left = p.n_units;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (tap < taps) {
+                            uint32_t a16 = patch16 + (uint32_t)p.tap_off[tap];
+                            for (int cb = 0; cb < p.n_cb; ++cb) {
+                                if (u_in_blk == 0) {
+                                    long long t3 = TCLK();
+                                    if (!pure) mbar_wait(&w_full[st], st_phase);
+                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                    m_wait_w += TCLK() - t3;
+                                    b16 = b016 + st * stage16;
+                                }
+                                for (int ks = 0; ks < ksteps; ++ks) {
+                                    umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);
+                                    umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);
+                                    acc = 1;
+                                    a16 += a_step16;
+                                    b16 += b_step16;
+                                }
+                                --units_left;
+                                if (++u_in_blk == p.upb || units_left == 0) {
+                                    if (leader && !pure) umma_commit(&w_empty[st]);  // frees the weight stage once these MMAs retire
+                                    u_in_blk = 0;
+                                    if (++st == (uint32_t)p.w_stages) { st = 0; st_phase ^= 1; }
+                                }
+                            }
                         }
                     }
                 }
-                if (leader) {
+                if (leader && !pure) {
                     umma_commit(&patch_empty[ps]);
                     umma_commit(&acc_full[as]);
                 }
                 __syncwarp();
+                if (++ps == (uint32_t)p.patch_stages) { ps = 0; ps_phase ^= 1; }
+                if (++as == (uint32_t)p.acc_stages) { as = 0; as_phase ^= 1; }
             }
-            if (p.dbg && blockIdx.x == 0 && leader) {
+            if (pure) {
+                if (leader) umma_commit(&acc_full[0]);
+                __syncwarp();
+                mbar_wait(&acc_full[0], 0);
+            }
+            if (DBG && p.dbg && blockIdx.x == 0 && leader) {
                 p.dbg[3] = m_wait_acc; p.dbg[4] = m_wait_patch; p.dbg[5] = m_wait_w; p.dbg[6] = TCLK() - m_total0; p.dbg[7] = it;
             }
         }
@@ -477,7 +500,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long tp1 = TCLK();
             const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.acc_stride);
-            for (int c0 = c_begin; c0 < ((p.dbg_flags & 2) ? c_begin : c_end); c0 += 16) {
+            for (int c0 = c_begin; c0 < (DFLAG(2) ? c_begin : c_end); c0 += 16) {
                 uint32_t v[16], v2[16];
                 tmem_ld16(trow + c0, v);                       // Ahi*Bhi + Alo*Bhi
                 tmem_ld16(trow + p.cout + c0, v2);             // Ahi*Blo
@@ -568,7 +591,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             mbar_arrive(&acc_empty[as]);                     // accumulator drained: the MMA warp may reuse it
             const long long tp2 = TCLK();
             e_p1 += tp2 - tp1;
-            if (staged && !(p.dbg_flags & 2)) {
+            if (staged && !DFLAG(2)) {
                 asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tile complete (epilogue warps only)
                 const long long tp3 = TCLK();
                 e_bar += tp3 - tp2;
@@ -590,7 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 e_bar += TCLK() - tp4;
             }
         }
-        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[12] = e_p2; }
+        if (DBG && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[12] = e_p2; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -674,6 +697,10 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     if (op.ksize == 1) { p.slots = TILE_M; p.pitch = 8; }
     else if (op.stride == 1) { p.pitch = TCT_W + 2; p.slots = (TCT_H + 2) * p.pitch; }
     else { p.pitch = TCT_W + 1; p.phase_slots = (TCT_H + 1) * p.pitch; p.slots = 4 * p.phase_slots; }
+    for (int t = 0; t < taps; ++t) {
+        const int ky = t / 3, kx = t % 3;
+        p.tap_off[t] = op.ksize == 1 ? 0 : op.stride == 1 ? ky * p.pitch + kx : ((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1);
+    }
     p.slots_p = p.slots + ((9 - (p.slots & 7)) & 7);                 // == 1 (mod 8): conflict-free chunk stride
     p.magic_chunks = magic_u32(op.cin / 8);
     p.magic_pitch = magic_u32(p.pitch);
@@ -716,9 +743,23 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     bool ok = false;
     for (int d : {64, 48, 32, 16}) {
         if (op.cin % d) continue;
-        p.kb_ch = d; p.n_cb = op.cin / d; p.n_kb = taps * p.n_cb;
-        p.stage_bytes = d * nb * 4;                                  // 2 planes x kb_ch x cout x 2 B
-        if ((!seg && plan(true)) || plan(false)) { ok = true; break; }
+        p.kb_ch = d; p.n_cb = op.cin / d; p.n_units = taps * p.n_cb;
+        p.unit_bytes = d * nb * 4;                                   // 2 planes x kb_ch x cout x 2 B
+        // units per weight block: resident -> as few blocks as barriers allow; streaming -> the largest block
+        // (fewest barrier round trips per tile) that still leaves two patch stages
+        auto set_upb = [&](int upb) {
+            p.upb = upb; p.n_kb = (p.n_units + upb - 1) / upb;
+            p.stage_bytes = upb * p.unit_bytes;
+        };
+        set_upb((p.n_units + MAX_WST - 1) / MAX_WST);
+        if (((!seg && plan(true)) || plan(false)) && p.resident) { ok = true; break; }
+        for (int stage_epi = seg ? 0 : 1; stage_epi >= 0 && !ok; --stage_epi)
+            for (int upb : {3, 2, 1}) {
+                if (upb > p.n_units) continue;
+                set_upb(upb);
+                if (plan(stage_epi != 0) && (upb == 1 || p.patch_stages >= 2)) { ok = true; break; }
+            }
+        if (ok) break;
     }
     if (!ok) return 0;
     p.fills_per_tile = p.resident ? 0 : p.n_kb / p.w_stages;
@@ -738,17 +779,23 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     }
     static bool attr_set = false;
     if (!attr_set) {
-        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
+    { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_PLAN"); f = e ? atoi(e) : 0; }
+      if (f) fprintf(stderr, "conv_tc plan: %dx%d s%d cin %d cout %d(+%d) %dx%d | %s kb_ch %d units %d upb %d blocks %d w_stages %d stage %d B | patches %d x %zu B | epi %d B | acc %d x %d cols | tiles %d grid %d smem %zu\n",
+                     op.ksize, op.ksize, op.stride, op.cin, nb, n0, p.H, p.W, p.resident ? "resident" : "stream", p.kb_ch, p.n_units, p.upb, p.n_kb,
+                     p.w_stages, p.stage_bytes, p.patch_stages, patch_bytes, p.epi_bytes, p.acc_stages, p.acc_stride, p.n_tiles, grid, smem); }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, p);
+    const bool dbg_kernel = p.dbg != nullptr || p.dbg_flags != 0;
+    cudaError_t e = dbg_kernel ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         lp_set_error("conv_tc launch failed: %s (smem %zu)", cudaGetErrorString(e), smem);
