@@ -419,6 +419,7 @@ template <typename F> static bool small_dispatch(int ks, int stride, int cin, in
     LP_SMALL(3, 2, 8, 16, false)
     LP_SMALL(3, 1, 8, 8, false)
     LP_SMALL(1, 1, 24, 16, false)
+    LP_SMALL(1, 1, 16, 16, false)
 #undef LP_SMALL
     return false;
 }
@@ -582,6 +583,7 @@ int lp_assign_small_slots(lp_net_plan& net, cudaStream_t st) {
         if (op.kind != LP_OP_STEM_U8 && op.kind != LP_OP_CONV) continue;
         const int nw = op.ksize * op.ksize * op.cin * op.cout;
         if (nw > SMALL_W_FLOATS || op.cout > 32 || next_slot >= SMALL_SLOTS) continue;
+        if (op.res_buf >= 0 || op.out_seg_len > 0 || op.out_cstride > 1) continue;      // shapes the small kernels do not cover
         bool have = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [](auto) {});
         if (!have) continue;
         const int slot = next_slot++;

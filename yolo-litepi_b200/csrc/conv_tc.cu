@@ -57,6 +57,8 @@ struct TcParams {
     int pitch;                 // patch row pitch in pixels (SBO_A = pitch * 16 B); 1x1: 8
     int phase_slots;           // stride 2: slots per parity phase
     int kb_ch, n_cb, n_kb;     // channels per K unit, channel blocks per tap, weight blocks per tile
+    unsigned magic_per_img, magic_tiles_x;   // tile -> (image, tile row, tile column) by multiply-high
+    float inv_hw_out;
     int tap_off[9];            // A start offset of each tap inside a patch, in 16-B slots (constant-bank operands of the issue loop)
     int n_units, upb, unit_bytes;   // K units (tap x channel block) per tile, units per weight block, bytes per unit
     int w_stages, stage_bytes, resident;
@@ -472,39 +474,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         const bool staged = p.epi_bytes > 0;
         asm volatile("griddepcontrol.wait;" ::: "memory");      // before any residual read / output write
         int it = 0;
-        long long e_wait = 0, e_total0 = TCLK(), e_p1 = 0, e_bar = 0, e_p2 = 0;
+        uint32_t as = 0, as_phase = 0;
+        long long e_wait = 0, e_total0 = TCLK(), e_p1 = 0, e_bar = 0, e_p2 = 0, e_ld = 0, e_pre = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int as = it % p.acc_stages;
-            const TileCoord tc = tile_coord(p, tile);
+            const long long e_top = TCLK();
             const int r = quad * 32 + lane;                  // accumulator row == TMEM lane == tile pixel
             bool valid;
             int oimg, opin;                                  // image and pixel-in-image of this row
             if (p.ksize == 1) {
-                const long long gp = tc.pix0 + r;
+                // hw_out <= 2^16 and the pixel index < 2^31: the float estimate is off by at most one
+                const long long gp = (long long)tile * TILE_M + r;
                 valid = gp < p.total_pix;
                 const unsigned gpu = valid ? (unsigned)gp : 0u;
-                oimg = (int)(gpu / (unsigned)hw_out);
-                opin = (int)(gpu - (unsigned)oimg * (unsigned)hw_out);
+                unsigned q = (unsigned)((float)gpu * p.inv_hw_out);
+                if (q * (unsigned)hw_out > gpu) --q;
+                if ((q + 1) * (unsigned)hw_out <= gpu) ++q;
+                oimg = (int)q;
+                opin = (int)(gpu - q * (unsigned)hw_out);
             } else {
-                const int oy = tc.oy0 + (r >> 3), ox = tc.ox0 + (r & 7);
+                const unsigned img = __umulhi((unsigned)tile, p.magic_per_img);
+                const unsigned rr = (unsigned)tile - img * (unsigned)(p.tiles_x * p.tiles_y);
+                const unsigned ty = __umulhi(rr, p.magic_tiles_x), tx = rr - ty * (unsigned)p.tiles_x;
+                const int oy = (int)ty * TCT_H + (r >> 3), ox = (int)tx * TCT_W + (r & 7);
                 valid = (oy < p.Ho && ox < p.Wo);
-                oimg = tc.img;
+                oimg = (int)img;
                 opin = oy * p.Wo + ox;
             }
             const long long obase = (long long)oimg * p.out_img + (long long)opin * p.out_C + p.out_coff;
             const long long rbase = (long long)oimg * p.res_img + (long long)opin * p.res_C + p.res_coff;
             if (staged && half == 0) row_base[r] = valid ? obase : -1;
             { long long t0 = TCLK();
-              mbar_wait(&acc_full[as], (it / p.acc_stages) & 1);
+              e_pre += t0 - e_top;
+              mbar_wait(&acc_full[as], as_phase);
               e_wait += TCLK() - t0; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long tp1 = TCLK();
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.acc_stride);
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + as * (uint32_t)p.acc_stride;
             for (int c0 = c_begin; c0 < (DFLAG(2) ? c_begin : c_end); c0 += 16) {
                 uint32_t v[16], v2[16];
                 tmem_ld16(trow + c0, v);                       // Ahi*Bhi + Alo*Bhi
                 tmem_ld16(trow + p.cout + c0, v2);             // Ahi*Blo
+                const long long tl0 = TCLK();
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                e_ld += TCLK() - tl0;
                 if (!valid) continue;
                 float f[16];
 #pragma unroll
@@ -589,6 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[as]);                     // accumulator drained: the MMA warp may reuse it
+            if (++as == (uint32_t)p.acc_stages) { as = 0; as_phase ^= 1; }
             const long long tp2 = TCLK();
             e_p1 += tp2 - tp1;
             if (staged && !DFLAG(2)) {
@@ -613,7 +626,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 e_bar += TCLK() - tp4;
             }
         }
-        if (DBG && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[12] = e_p2; }
+        if (DBG && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[12] = e_p2; p.dbg[13] = e_ld; p.dbg[14] = e_pre; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -769,6 +782,7 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     while (p.tmem_cols < p.acc_stages * p.acc_stride) p.tmem_cols <<= 1;
     const size_t smem = 512 + (size_t)p.patch_stages * patch_bytes + (size_t)p.w_stages * p.stage_bytes + p.tab_bytes + p.mtab_bytes + p.epi_bytes;
 
+    p.inv_hw_out = 1.0f / (float)(p.Ho * p.Wo);
     if (op.ksize == 1) {
         p.total_pix = (long long)batch * ib.h * ib.w;
         p.n_tiles = (int)((p.total_pix + TILE_M - 1) / TILE_M);
@@ -776,6 +790,8 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         p.tiles_x = (p.Wo + TCT_W - 1) / TCT_W;
         p.tiles_y = (p.Ho + TCT_H - 1) / TCT_H;
         p.n_tiles = p.tiles_x * p.tiles_y * batch;
+        p.magic_per_img = magic_u32(p.tiles_x * p.tiles_y);
+        p.magic_tiles_x = magic_u32(p.tiles_x);
     }
     static bool attr_set = false;
     if (!attr_set) {
