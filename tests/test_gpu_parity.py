@@ -352,3 +352,57 @@ def test_full_batch_properties(lp, v1_paths, clf):
     one = pipe.run_batch([frames[17]], 0.25, 0.45, 50)[0]
     assert [d["bbox"] for d in got[17]] == [d["bbox"] for d in one]
     assert [d["cls_class"] for d in got[17]] == [d["cls_class"] for d in one]
+
+
+def test_config3_tt100k_dense_batch(lp, v1_paths):
+    """BASELINE configs[2] shape: 32 frames of 2048x2048 with dense small signs, 91 classes.  Two frames are
+    checked against the oracle end to end; at full size the batch must equal its per-frame runs, every ROI
+    must be a valid integer box of the frame, and records must survive the shard/gather/sort round trip."""
+    from litepi_b200 import synth, runner
+    ref = PR.build_shufflenet(91, seed=3)
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=91, max_batch=32,
+                           classifier_state_dict=ref.state_dict(), seed=0)
+    orc = DetectorOracle(v1_paths[0], v1_paths[1], seed=0)
+    _sync(orc, pipe.detector.model)
+    frames = [synth.tt_frame(i) for i in range(32)]
+    got = pipe.run_batch(frames, 0.25, 0.45, 50)
+    assert sum(len(g) for g in got) > 32 * 5                       # dense: well over 5 signs per frame survive
+    for i in (0, 19):
+        _compare(got[i], oracle_pipeline_run(orc, ref, frames[i], 0.25, 0.45, 50))
+    for i in (3, 31):
+        one = pipe.run_batch([frames[i]], 0.25, 0.45, 50)[0]
+        assert [d["bbox"] for d in one] == [d["bbox"] for d in got[i]]
+        assert [d["cls_class"] for d in one] == [d["cls_class"] for d in got[i]]
+    for g in got:
+        for d in g:
+            x1, y1, x2, y2 = d["bbox"]
+            assert all(isinstance(v, (int, np.integer)) for v in d["bbox"]) and 0 <= d["cls_class"] < 91   # e2e.py:522 yields numpy ints
+            assert x2 >= x1 and y2 >= y1 and x1 >= 0 and y1 >= 0 and x2 <= 2048 and y2 <= 2048    # postprocess clips to the frame
+    whole = runner.run_sharded(pipe, frames, 0.25, 0.45, 50, 0, 1)
+    parts = runner.sort_records(np.concatenate([runner.run_sharded(pipe, frames, 0.25, 0.45, 50, r, 8) for r in range(8)]))
+    assert np.array_equal(whole, parts)
+
+
+def test_config4_classifier_1024_crops(lp):
+    """BASELINE configs[3]: ShuffleNetV2 alone on 1024 crops (the 15 real debug_rois of the reference + synthetic
+    glyph crops of 10..90 px): Pillow-exact resize, logits within 1e-2 and top-1 equal to torchvision for all."""
+    import cv2
+    from litepi_b200 import synth
+    ref = PR.build_shufflenet(49, seed=4)
+    c = lp.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=ref.state_dict(), max_batch=1024)
+    real = [cv2.imread(p) for p in debug_roi_paths()]
+    assert len(real) == 15 and all(r is not None for r in real)
+    crops = real + synth.roi_crops(1024 - len(real), seed=7)
+    u8 = np.stack([PR.classifier_input_ref(cr)[0] for cr in crops])
+    assert np.array_equal(c.preprocess_batch(crops).cpu().numpy(), u8)      # K6 bit-exact on all 1024
+    lg = c.logits_for(u8)
+    x = (torch.from_numpy(u8.astype(np.float32)) / 255 - 0.18) / 0.34
+    with torch.no_grad():
+        rl = ref(x.permute(0, 3, 1, 2)).numpy()
+    assert np.abs(lg - rl).max() < LOGIT_TOL
+    assert np.array_equal(lg.argmax(1), rl.argmax(1))
+    cls, probs = c.predict_batch(crops)
+    assert np.array_equal(cls, rl.argmax(1)) and np.allclose(probs.sum(1), 1.0, atol=1e-5)
+    # composition invariance: any sub-batch gives the same rows
+    cls2, probs2 = c.predict_batch(crops[100:133])
+    assert np.array_equal(cls2, cls[100:133]) and np.abs(probs2 - probs[100:133]).max() < 1e-6
