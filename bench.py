@@ -242,14 +242,23 @@ def main():
     launches0 = pipe.counters.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_rois = 0
-    all_records = []
+    rec_ring = torch.empty((args.steps,) + tuple(pipe.records.shape), dtype=torch.int32, device=dev)
+    cnt_ring = torch.zeros((args.steps,), dtype=torch.int32, device=dev)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        n = pipe.run_device(fb0, CONF, IOU, MIN_AREA, frame_ids)
-        n_rois += n
-        all_records.append(pipe.records[:n].clone())
-    local = torch.cat(all_records) if all_records else torch.zeros((0, 9), dtype=torch.int32, device=dev)
+    # steps are enqueued back to back: the ROI count stays on the device (lp_set_roi_count_device), so a step
+    # needs no host round trip; each step's records and count are kept on the device for the final gather
+    for k in range(args.steps):
+        pipe.enqueue_device(fb0, CONF, IOU, MIN_AREA, frame_ids)
+        rec_ring[k].copy_(pipe.records, non_blocking=True)          # preallocated: no allocator call (= no implicit sync) in the timed region
+        cnt_ring[k:k + 1].copy_(pipe.n_rois, non_blocking=True)
+    pipe.finish(fb0, frame_ids)                          # waits; validates capacities of the last step
+    counts_h = cnt_ring.cpu().tolist()
+    if counts_h and max(counts_h) > pipe.max_rois:
+        raise RuntimeError("bench: a step exceeded max_rois")
+    n_rois = sum(counts_h)
+    local = (torch.cat([rec_ring[k, :c] for k, c in enumerate(counts_h)]) if counts_h
+             else torch.zeros((0, 9), dtype=torch.int32, device=dev))
     gathered = gather_records(local)                    # the one collective: final detection gather (NCCL)
     e1.record()
     barrier()
@@ -277,6 +286,8 @@ def main():
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    n_out = [0]
+
     def e2e_loop(steps):
         d2h = 0
         main_stream = torch.cuda.current_stream()
@@ -292,10 +303,16 @@ def main():
                     dev_frames[nxt].copy_(host, non_blocking=True)
                     ready[nxt].record(copy_stream)
             main_stream.wait_event(ready[cur])
-            n = pipe.run_device(fbs[cur], CONF, IOU, MIN_AREA, frame_ids)
+            pipe.enqueue_device(fbs[cur], CONF, IOU, MIN_AREA, frame_ids, slot=cur)
             consumed[cur].record(main_stream)
-            rec = pipe.fetch_records(n)
-            d2h += rec.nbytes + 4 + 4 * B
+            pipe.enqueue_fetch(cur)                      # D2H of the step's records, queued behind the step
+            if s >= 1:
+                rec = pipe.collect(nxt)                  # read step s-1 back while step s runs
+                n_out[0] += rec.shape[0]
+            d2h += pipe.records.numel() * 4 + 4 + 4 * B
+        if steps:
+            rec = pipe.collect((steps - 1) % 2)
+            n_out[0] += rec.shape[0]
         return d2h
 
     e2e_loop(args.warmup)

@@ -37,7 +37,7 @@ extern "C" {
 
 typedef struct lp_ctx lp_ctx;
 
-#define LP_ABI_VERSION 2
+#define LP_ABI_VERSION 3
 
 /* ---- network plan (built on the host from the reference's model.ncnn.param) ---- */
 
@@ -168,6 +168,14 @@ int lp_pack_records(lp_ctx* ctx, const int32_t* roi_src, const int32_t* frame_id
                     const float* boxes, const float* scores, const int64_t* classes, int max_det,
                     const int64_t* cls_argmax, const float* probs, int n_classes, int n_rois,
                     int32_t* records, void* stream);
+
+/* Device-side ROI count.  The reference sizes its classifier batches on the host (len(rois),
+ * e2e.py:477-485); a GPU pipeline would have to read the count back in the middle of a step and
+ * leave the device idle meanwhile.  After this call with a non-null pointer (the int32 that
+ * lp_roi_select writes), lp_roi_resize / lp_classify (fused classifier only) / lp_pack_records
+ * treat their count argument as a CAPACITY and process min(*n_rois_dev, capacity) ROIs, so a whole
+ * step is enqueued without a host synchronisation.  Null restores host counts. */
+int lp_set_roi_count_device(lp_ctx* ctx, const int32_t* n_rois_dev);
 
 /* Workspace bytes lp_detect_forward / lp_classify need for the loaded plan (0 if not loaded). */
 size_t lp_workspace_bytes(lp_ctx* ctx, int net);

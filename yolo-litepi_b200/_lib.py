@@ -16,7 +16,7 @@ OP_STEM_U8, OP_CONV, OP_DWCONV3, OP_MAXPOOL, OP_UPSAMPLE2, OP_COPY, OP_MEAN_FC =
 ACT_NONE, ACT_SILU, ACT_RELU = range(3)
 FMT_SPLIT16, FMT_F32, FMT_U8 = range(3)
 NET_DETECTOR, NET_CLASSIFIER = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class BufDesc(C.Structure):
@@ -65,6 +65,7 @@ _PROTOS = {
                               C.c_void_p, C.c_void_p]),
     "lp_pack_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "lp_set_roi_count_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lp_launch_count": (C.c_int64, [C.c_void_p]),
     "lp_debug_tc_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lp_probe_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

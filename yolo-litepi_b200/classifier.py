@@ -74,7 +74,7 @@ class B200Classifier:
                     "lp_net_load(classifier)")
         # the production path: the whole network in one persistent kernel (csrc/shufflenet_fused.cu); the
         # layer-by-layer plan above stays loaded as the cross-check (set_fused(False))
-        self.fused = bool(fused) and self.input_size == 64
+        self.fused = self._has_fused = bool(fused) and self.input_size == 64
         if self.fused:
             steps, fw, n_front, n_back, smem = build_fused_classifier(sd, group=fused_group, in_size=self.input_size)
             with torch.cuda.device(self.device):
@@ -88,6 +88,7 @@ class B200Classifier:
 
     def set_fused(self, enable: bool):
         L.check(L.lib().lp_set_fused_classifier(self.ctx.handle, 1 if enable else 0))
+        self.fused = bool(enable) and self._has_fused
 
     def _alloc(self, n: int):
         if n <= self._cap:

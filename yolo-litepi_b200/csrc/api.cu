@@ -165,6 +165,12 @@ extern "C" int lp_detect_forward(lp_ctx* ctx, const uint8_t* in, int batch, void
     return lp_launch_detect_tail(ctx, (const float*)((uint8_t*)workspace + hb.offset), batch, hb.c, out0, st);
 }
 
+extern "C" int lp_set_roi_count_device(lp_ctx* ctx, const int32_t* n_rois_dev) {
+    LP_CHECK(ctx, "lp_set_roi_count_device: null context");
+    ctx->roi_count_dev = n_rois_dev;
+    return 0;
+}
+
 extern "C" int lp_classify(lp_ctx* ctx, const uint8_t* in, int n, void* workspace, size_t workspace_bytes,
                            float* logits, float* probs, int64_t* argmax, void* stream) {
     LP_CHECK(ctx && workspace && logits && probs && argmax, "lp_classify: null argument");
@@ -179,6 +185,7 @@ extern "C" int lp_classify(lp_ctx* ctx, const uint8_t* in, int n, void* workspac
         if (r < 0) return r;
         if (r == 1) return lp_launch_softmax_argmax(ctx, logits, n, C, probs, argmax, st);
     }
+    LP_CHECK(ctx->roi_count_dev == nullptr, "lp_classify: a device-side ROI count needs the fused classifier");
     const size_t img_bytes = (size_t)P.bufs[P.ops[0].in_buf].h * P.bufs[P.ops[0].in_buf].w * 3;
     for (int base = 0; base < n; base += P.max_batch) {
         const int nb = n - base < P.max_batch ? n - base : P.max_batch;

@@ -65,6 +65,7 @@ struct lp_ctx {
     int fused_slot = -1;             // index into the fused-classifier table (shufflenet_fused.cu)
     int use_fused = 1;
     int use_pdl = 1;                 // programmatic dependent launch between tensor-core conv kernels (env LP_NO_PDL=1 disables)
+    const int* roi_count_dev = nullptr;   // lp_set_roi_count_device: ROI-side calls take their count from the device
     long long* tc_dbg = nullptr;     // device buffer (16 x int64) for conv_tc role timing; debugging only
 };
 #define LP_PROBE_RING 512

@@ -380,9 +380,9 @@ __global__ void pack_records_kernel(const int* __restrict__ roi_src, const int* 
                                     const float* __restrict__ boxes, const float* __restrict__ scores,
                                     const long long* __restrict__ classes, int max_det,
                                     const long long* __restrict__ cls_argmax, const float* __restrict__ probs,
-                                    int n_classes, int n_rois, int* __restrict__ rec) {
+                                    int n_classes, int n_rois, const int* __restrict__ n_dev, int* __restrict__ rec) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rois) return;
+    if (r >= n_rois || (n_dev && r >= *n_dev)) return;
     const int img = roi_src[2 * r], k = roi_src[2 * r + 1];
     const long long o = (long long)img * max_det + k;
     int* q = rec + (long long)r * 9;
@@ -403,7 +403,7 @@ extern "C" int lp_pack_records(lp_ctx* ctx, const int32_t* roi_src, const int32_
     if (n_rois <= 0) return 0;
     pack_records_kernel<<<(n_rois + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         roi_src, frame_ids, boxes, scores, (const long long*)classes, max_det, (const long long*)cls_argmax, probs,
-        n_classes, n_rois, records);
+        n_classes, n_rois, ctx->roi_count_dev, records);
     LP_LAUNCH_OK(ctx);
     return 0;
 }

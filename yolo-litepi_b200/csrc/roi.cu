@@ -59,7 +59,7 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 // Block per ROI.  Shared memory: coefficient tables for both axes + a ring of horizontally
 // resampled rows (u8, S*3 bytes each).
 __global__ void __launch_bounds__(256) roi_resize_kernel(RoiFrames fr, int img_base, const int* __restrict__ roi_xyxy,
-                                                         const int* __restrict__ roi_src, int n_rois, int S, int kmax,
+                                                         const int* __restrict__ roi_src, int n_rois, const int* __restrict__ n_dev, int S, int kmax,
                                                          int tmp_rows, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     int* kx = reinterpret_cast<int*>(smem);            // [S][kmax]
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) roi_resize_kernel(RoiFrames fr, int img_b
     int* s_misc = by + S * 2;                          // [4]
     uint8_t* tmp = reinterpret_cast<uint8_t*>(s_misc + 4);   // [tmp_rows][S*3]
     const int r = blockIdx.x;
-    if (r >= n_rois) return;
+    if (r >= n_rois || (n_dev && r >= *n_dev)) return;
     const int img = roi_src[2 * r] - img_base;
     if (img < 0 || img >= LP_MAX_TABLE) return;        // ROI of another 64-image launch chunk
     const int x1 = roi_xyxy[4 * r], y1 = roi_xyxy[4 * r + 1], x2 = roi_xyxy[4 * r + 2], y2 = roi_xyxy[4 * r + 3];
@@ -152,7 +152,7 @@ extern "C" int lp_roi_resize(lp_ctx* ctx, const uint8_t* const* frames_h, const 
         RoiFrames fr;
         for (int i = 0; i < n; ++i) { fr.ptr[i] = frames_h[base + i]; fr.pitch[i] = pitch_h[base + i]; }
         for (int i = n; i < LP_MAX_TABLE; ++i) { fr.ptr[i] = nullptr; fr.pitch[i] = 0; }
-        roi_resize_kernel<<<n_rois, 256, smem, st>>>(fr, base, roi_xyxy, roi_src, n_rois, out_size, kmax, tmp_rows, out);
+        roi_resize_kernel<<<n_rois, 256, smem, st>>>(fr, base, roi_xyxy, roi_src, n_rois, ctx->roi_count_dev, out_size, kmax, tmp_rows, out);
         LP_LAUNCH_OK(ctx);
     }
     return 0;
@@ -162,10 +162,10 @@ extern "C" int lp_roi_resize(lp_ctx* ctx, const uint8_t* const* frames_h, const 
 // softmax + argmax over classifier logits (torch.softmax(dim=1), np.argmax; e2e.py:394-396).
 // One warp per ROI.
 // ---------------------------------------------------------------------------------------------
-__global__ void softmax_argmax_kernel(const float* __restrict__ logits, int n, int C, float* __restrict__ probs,
-                                      long long* __restrict__ argmax) {
+__global__ void softmax_argmax_kernel(const float* __restrict__ logits, int n, const int* __restrict__ n_dev, int C,
+                                      float* __restrict__ probs, long long* __restrict__ argmax) {
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (r >= n) return;
+    if (r >= n || (n_dev && r >= *n_dev)) return;
     const float* x = logits + (long long)r * C;
     float m = -INFINITY;
     for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
@@ -193,7 +193,7 @@ __global__ void softmax_argmax_kernel(const float* __restrict__ logits, int n, i
 
 int lp_launch_softmax_argmax(lp_ctx* ctx, const float* logits, int n, int C, float* probs, int64_t* argmax, cudaStream_t st) {
     if (n <= 0) return 0;
-    softmax_argmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(logits, n, C, probs, (long long*)argmax);
+    softmax_argmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(logits, n, ctx->roi_count_dev, C, probs, (long long*)argmax);
     LP_LAUNCH_OK(ctx);
     return 0;
 }

@@ -169,7 +169,7 @@ __device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C,
 }
 
 __global__ void __launch_bounds__(FUSED_BLOCK, 1)
-shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float* __restrict__ W,
+shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const int* __restrict__ n_dev, const float* __restrict__ W,
                         const FStep* __restrict__ steps, int n_front, int n_back, int G, int in_hw,
                         float mean, float stdv, float* __restrict__ logits, int n_classes, int wbuf_off,
                         long long* dbg, int cs) {
@@ -192,6 +192,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois, const float*
     __syncthreads();
     f_cluster_sync();                                        // every CTA's barriers exist before any remote arrive / multicast
     const int img_bytes = in_hw * in_hw * 3;
+    const int n_rois = n_dev ? min(n_rois_cap, *n_dev) : n_rois_cap;     // count produced on the device by roi_select
     const int n_groups = (n_rois + G - 1) / G;
     // every CTA of a cluster runs the same number of iterations (the weight stream is shared); CTAs whose
     // group index is past the end compute on stale data and write nothing
@@ -477,7 +478,7 @@ int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cuda
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
+    cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, ctx->roi_count_dev, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
                                         f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, ctx->tc_dbg, cs);
     if (le != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(le)); return -2; }
     ctx->launches++;

@@ -77,29 +77,70 @@ class B200Pipeline:
             self.roi_src = torch.empty((R, 2), dtype=torch.int32, device=self.device)
             self.n_rois = torch.zeros((1,), dtype=torch.int32, device=self.device)
             self.records = torch.empty((R, REC_WORDS), dtype=torch.int32, device=self.device)
-            self.n_rois_h = torch.zeros((1,), dtype=torch.int32).pin_memory()
-            self.records_h = torch.empty((R, REC_WORDS), dtype=torch.int32).pin_memory()
-            self.counts_h = torch.zeros((self.max_batch,), dtype=torch.int32).pin_memory()
+            # host mirrors are double-buffered ("slots") so step s+1 can be enqueued while step s is read back
+            self._n_rois_h = [torch.zeros((1,), dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._records_h = [torch.empty((R, REC_WORDS), dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._counts_h = [torch.zeros((self.max_batch,), dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._fetched = [torch.cuda.Event() for _ in range(2)]
+            self._pending = [0, 0]
 
     # ------------------------------------------------------------------ device path
-    def run_device(self, fb: FrameBatch, conf_threshold: float = 0.5, iou_threshold: float = 0.45,
-                   min_area: int = 100, frame_ids: Optional[torch.Tensor] = None) -> int:
-        """Whole hot path on device-resident frames.  Returns the ROI count; records for them are in
-        ``self.records[:n]`` (device).  One tiny D2H (the ROI count) sizes the classifier launches."""
+    def enqueue_device(self, fb: FrameBatch, conf_threshold: float = 0.5, iou_threshold: float = 0.45,
+                       min_area: int = 100, frame_ids: Optional[torch.Tensor] = None, slot: int = 0) -> None:
+        """Enqueue the whole hot path for device-resident frames WITHOUT a host synchronisation: the ROI
+        count stays on the device (lp_set_roi_count_device) and the ROI-side kernels are launched at
+        capacity ``max_rois``.  ``finish`` waits and validates; records are in ``self.records`` (device)."""
         det, clf, lib = self.detector, self.classifier, L.lib()
         det.detect_device(fb, conf_threshold, iou_threshold)
         L.check(lib.lp_roi_select(self.ctx.handle, _ptr(det.boxes), _ptr(det.counts), det.max_det, fb.h, fb.w, fb.n,
                                   int(min_area), self.max_rois, _ptr(self.roi_xyxy), _ptr(self.roi_src),
                                   _ptr(self.n_rois), _stream()), "lp_roi_select")
-        self.n_rois_h.copy_(self.n_rois, non_blocking=True)
-        self.counts_h[:fb.n].copy_(det.counts[:fb.n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        n = int(self.n_rois_h[0])
+        self._n_rois_h[slot].copy_(self.n_rois, non_blocking=True)
+        self._counts_h[slot][:fb.n].copy_(det.counts[:fb.n], non_blocking=True)
+        self._pending[slot] = fb.n
+        if not clf.fused:
+            return                                    # layer-by-layer classifier: sized on the host in finish()
+        cap = self.max_rois
+        for ctx in (clf.ctx, self.ctx):
+            L.check(lib.lp_set_roi_count_device(ctx.handle, _ptr(self.n_rois)), "lp_set_roi_count_device")
+        try:
+            cls_in = clf.resize_device(fb, self.roi_xyxy, self.roi_src, cap)
+            clf.classify_device(cls_in)
+            L.check(lib.lp_pack_records(self.ctx.handle, _ptr(self.roi_src), _ptr(frame_ids), _ptr(det.boxes),
+                                        _ptr(det.scores), _ptr(det.classes), det.max_det, _ptr(clf.argmax),
+                                        _ptr(clf.probs), clf.num_classes, cap, _ptr(self.records), _stream()),
+                    "lp_pack_records")
+        finally:
+            for ctx in (clf.ctx, self.ctx):
+                lib.lp_set_roi_count_device(ctx.handle, None)
+
+    def _validate(self, slot: int) -> int:
+        n, nf = int(self._n_rois_h[slot][0]), int(self._pending[slot])
         if n > self.max_rois:
             raise RuntimeError(f"litepi_b200: {n} ROIs exceed max_rois={self.max_rois}")
-        if fb.n and int(self.counts_h[:fb.n].max()) > det.max_det:
-            raise RuntimeError(f"litepi_b200: a frame has more than max_det={det.max_det} detections")
-        if n:
+        if nf and int(self._counts_h[slot][:nf].max()) > self.detector.max_det:
+            raise RuntimeError(f"litepi_b200: a frame has more than max_det={self.detector.max_det} detections")
+        return n
+
+    def enqueue_fetch(self, slot: int = 0) -> None:
+        """Queue the D2H copy of the step's records (capacity-sized: the count is not known on the host yet)
+        behind the step on the current stream; ``collect(slot)`` waits for it."""
+        self._records_h[slot].copy_(self.records, non_blocking=True)
+        self._fetched[slot].record(torch.cuda.current_stream())
+
+    def collect(self, slot: int = 0) -> np.ndarray:
+        """Records of the step enqueued with ``slot`` (after ``enqueue_fetch``), as a [n, 9] int32 array."""
+        self._fetched[slot].synchronize()
+        n = self._validate(slot)
+        return self._records_h[slot][:n].numpy().copy()
+
+    def finish(self, fb: Optional[FrameBatch] = None, frame_ids: Optional[torch.Tensor] = None, slot: int = 0) -> int:
+        """Wait for the enqueued step; returns its ROI count.  Capacity overruns fail loudly here."""
+        det, clf, lib = self.detector, self.classifier, L.lib()
+        torch.cuda.current_stream().synchronize()
+        n = self._validate(slot)
+        if n and not clf.fused:
+            assert fb is not None, "finish(fb) is required with the layer-by-layer classifier"
             cls_in = clf.resize_device(fb, self.roi_xyxy, self.roi_src, n)
             clf.classify_device(cls_in)
             L.check(lib.lp_pack_records(self.ctx.handle, _ptr(self.roi_src), _ptr(frame_ids), _ptr(det.boxes),
@@ -108,13 +149,20 @@ class B200Pipeline:
                     "lp_pack_records")
         return n
 
+    def run_device(self, fb: FrameBatch, conf_threshold: float = 0.5, iou_threshold: float = 0.45,
+                   min_area: int = 100, frame_ids: Optional[torch.Tensor] = None) -> int:
+        """Whole hot path on device-resident frames.  Returns the ROI count; records for them are in
+        ``self.records[:n]`` (device)."""
+        self.enqueue_device(fb, conf_threshold, iou_threshold, min_area, frame_ids)
+        return self.finish(fb, frame_ids)
+
     def fetch_records(self, n: int) -> np.ndarray:
         """D2H of ``n`` packed records -> structured numpy view [n] (blocking)."""
         if n == 0:
             return np.zeros((0, REC_WORDS), np.int32)
-        self.records_h[:n].copy_(self.records[:n], non_blocking=True)
+        self._records_h[0][:n].copy_(self.records[:n], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.records_h[:n].numpy().copy()
+        return self._records_h[0][:n].numpy().copy()
 
     @staticmethod
     def records_to_results(rec: np.ndarray, n_frames: int) -> List[List[Dict]]:
