@@ -344,6 +344,13 @@ def main():
     dom_ms = statistics.mean(probe) if probe else None
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms else None
     peak = pk["bf16_tflops_sustained"]
+    traffic = None                                   # measured once with ncu --set full for this kernel at this workload
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("kernel") == pipe.detector.plan.names[dom] and B == 64:
+            traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -359,7 +366,8 @@ def main():
         "gpu_launches": int(launches),
         "p50_latency_ms": p50,
         "roofline": {"bound": "tensor", "kernel": pipe.detector.plan.names[dom], "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/dominant_kernel_traffic.json)",
                      "peak_source": pk_src + " bf16_tflops_sustained", "launch_ms": dom_ms,
                      "flops_per_launch": dom_flops},
     }
