@@ -402,11 +402,18 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, 
         }
     }
     const long long opix = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff;
+    const long long rpix = (long long)img * p.res.img + ((long long)oy * p.Wo + ox) * p.res.C + p.res.coff;
 #pragma unroll
     for (int g = 0; g < COUT / 8; ++g) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = act_apply(acc[g * 8 + i], p.act);
+        if (p.res.base) {                              // C2f bottleneck shortcut: added after the activation
+            float r[8];
+            ld8(p.res, rpix + g * 8, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += r[i];
+        }
         st8(p.out, opix + g * 8, v);
     }
 }
@@ -551,6 +558,48 @@ __global__ void maxpool8_kernel(ConvParams p) {
     st8(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + ch * 8, m);
 }
 
+// SPPF: three cascaded 5x5 stride-1 max pools (= 5x5, 9x9, 13x13 windows) of one 8-channel chunk of one
+// image per block, the map held in shared memory; writes the three pooled slices next to each other in
+// the concat buffer.  Replaces three launches that each re-read the map from L2.
+__global__ void __launch_bounds__(256) sppf3_kernel(ConvParams p, int slice_stride) {
+    extern __shared__ float s_map[];                    // [2][H*W][8]
+    const int hw = p.H * p.W;
+    float* a = s_map;
+    float* b = s_map + hw * 8;
+    const int cpp = p.cout >> 3;
+    const int img = blockIdx.x / cpp, ch = blockIdx.x - img * cpp;
+    const long long in0 = (long long)img * p.in.img + p.in.coff + ch * 8;
+    for (int px = threadIdx.x; px < hw; px += blockDim.x) {
+        float v[8];
+        ld8(p.in, in0 + (long long)px * p.in.C, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[px * 8 + k] = v[k];
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int e = threadIdx.x; e < hw * 8; e += blockDim.x) {
+            const int px = e >> 3, k = e & 7;
+            const int oy = px / p.W, ox = px - oy * p.W;
+            float m = -INFINITY;
+            for (int ky = -2; ky <= 2; ++ky) {
+                const int iy = oy + ky;
+                if (iy < 0 || iy >= p.H) continue;
+                for (int kx = -2; kx <= 2; ++kx) {
+                    const int ix = ox + kx;
+                    if (ix < 0 || ix >= p.W) continue;
+                    m = fmaxf(m, a[(iy * p.W + ix) * 8 + k]);
+                }
+            }
+            b[e] = m;
+        }
+        __syncthreads();
+        const long long out0 = (long long)img * p.out.img + p.out.coff + (long long)pass * slice_stride + ch * 8;
+        for (int px = threadIdx.x; px < hw; px += blockDim.x) st8(p.out, out0 + (long long)px * p.out.C, b + px * 8);
+        float* t = a; a = b; b = t;
+        __syncthreads();
+    }
+}
+
 // global mean over HxW then FC: logits[img][j] = bias[j] + sum_c mean_c * w[c][j]   (w stored [cin][cout])
 __global__ void mean_fc_kernel(ConvParams p, float* __restrict__ logits) {
     extern __shared__ float s_mean[];
@@ -577,20 +626,34 @@ __global__ void mean_fc_kernel(ConvParams p, float* __restrict__ logits) {
 // generic kernel.
 int lp_assign_small_slots(lp_net_plan& net, cudaStream_t st) {
     static int next_slot = 0;
+    static uint64_t slot_key[SMALL_SLOTS];             // content hash of what each slot holds: equal layers share a slot
     net.small_slot.assign(net.ops.size(), -1);
+    std::vector<float> host(SMALL_SLOT_FLOATS);
     for (size_t i = 0; i < net.ops.size(); ++i) {
         const lp_op_desc& op = net.ops[i];
         if (op.kind != LP_OP_STEM_U8 && op.kind != LP_OP_CONV) continue;
         const int nw = op.ksize * op.ksize * op.cin * op.cout;
-        if (nw > SMALL_W_FLOATS || op.cout > 32 || next_slot >= SMALL_SLOTS) continue;
-        if (op.res_buf >= 0 || op.out_seg_len > 0 || op.out_cstride > 1) continue;      // shapes the small kernels do not cover
+        if (nw > SMALL_W_FLOATS || op.cout > 32) continue;
+        if (op.out_seg_len > 0 || op.out_cstride > 1) continue;      // shapes the small kernels do not cover
         bool have = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [](auto) {});
         if (!have) continue;
-        const int slot = next_slot++;
-        LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.w_off, (size_t)nw * 4, (size_t)slot * SMALL_SLOT_FLOATS * 4,
-                                        cudaMemcpyDeviceToDevice, st));
-        LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.b_off, (size_t)op.cout * 4,
-                                        ((size_t)slot * SMALL_SLOT_FLOATS + SMALL_W_FLOATS) * 4, cudaMemcpyDeviceToDevice, st));
+        LP_CUDA(cudaMemcpyAsync(host.data(), net.weights + op.w_off, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        LP_CUDA(cudaMemcpyAsync(host.data() + nw, net.weights + op.b_off, (size_t)op.cout * 4, cudaMemcpyDeviceToHost, st));
+        LP_CUDA(cudaStreamSynchronize(st));
+        uint64_t key = 1469598103934665603ull ^ ((uint64_t)op.ksize << 48 | (uint64_t)op.stride << 40 | (uint64_t)op.cin << 20 | (uint64_t)op.cout);
+        const uint8_t* hb = reinterpret_cast<const uint8_t*>(host.data());
+        for (size_t b = 0; b < (size_t)(nw + op.cout) * 4; ++b) { key ^= hb[b]; key *= 1099511628211ull; }
+        int slot = -1;
+        for (int s2 = 0; s2 < next_slot; ++s2) if (slot_key[s2] == key) { slot = s2; break; }
+        if (slot < 0) {
+            if (next_slot >= SMALL_SLOTS) continue;                  // out of constant memory: generic kernel
+            slot = next_slot++;
+            slot_key[slot] = key;
+            LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.w_off, (size_t)nw * 4, (size_t)slot * SMALL_SLOT_FLOATS * 4,
+                                            cudaMemcpyDeviceToDevice, st));
+            LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.b_off, (size_t)op.cout * 4,
+                                            ((size_t)slot * SMALL_SLOT_FLOATS + SMALL_W_FLOATS) * 4, cudaMemcpyDeviceToDevice, st));
+        }
         net.small_slot[i] = slot;
     }
     LP_CUDA(cudaStreamSynchronize(st));
@@ -671,7 +734,8 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
         }
         const long long total = (long long)batch * p.Ho * p.Wo * p.cout;
         if ((op.kind == LP_OP_STEM_U8 || op.kind == LP_OP_CONV) && net.small_slot.size() > oi && net.small_slot[oi] >= 0 &&
-            p.res.base == nullptr && p.seg_len == 0 && p.out_cstride == 1 && p.out.fmt == LP_FMT_SPLIT16 &&
+            (p.res.base == nullptr || (p.res.fmt == LP_FMT_SPLIT16 && p.res.coff % 8 == 0)) && p.seg_len == 0 &&
+            p.out_cstride == 1 && p.out.fmt == LP_FMT_SPLIT16 &&
             (op.kind == LP_OP_STEM_U8 || p.in.fmt == LP_FMT_SPLIT16) && p.in.coff % 8 == 0 && p.out.coff % 8 == 0) {
             const int slot = net.small_slot[oi];
             const bool ran = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [&](auto kern) {
@@ -710,6 +774,23 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
         case LP_OP_MAXPOOL: {
             const bool v8 = p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16 && p.cout % 8 == 0 &&
                             p.in.coff % 8 == 0 && p.out.coff % 8 == 0 && p.out_cstride == 1 && p.seg_len == 0;
+            // SPPF cascade: this 5x5 s1 pool feeds a second and a third one, all slices of one buffer
+            if (v8 && op.ksize == 5 && op.stride == 1 && oi + 2 < net.ops.size() &&
+                !(ctx->probe_net == net_id && (ctx->probe_op == -2 || (ctx->probe_op >= (int)oi && ctx->probe_op <= (int)oi + 2))) &&
+                (size_t)p.H * p.W * 64 <= 48 * 1024) {
+                const lp_op_desc& o1 = net.ops[oi + 1];
+                const lp_op_desc& o2 = net.ops[oi + 2];
+                const int step = o1.out_coff - op.out_coff;
+                auto chained = [&](const lp_op_desc& a, const lp_op_desc& b) {
+                    return b.kind == LP_OP_MAXPOOL && b.ksize == 5 && b.stride == 1 && b.cout == a.cout && b.in_buf == a.out_buf &&
+                           b.in_coff == a.out_coff && b.out_buf == a.out_buf && b.out_seg_len == 0 && b.out_cstride <= 1;
+                };
+                if (chained(op, o1) && chained(o1, o2) && o2.out_coff - o1.out_coff == step && step >= op.cout) {
+                    sppf3_kernel<<<batch * (p.cout / 8), 256, (size_t)p.H * p.W * 64, st>>>(p, step);
+                    oi += 2;                          // the two downstream pools are done
+                    break;
+                }
+            }
             if (v8) maxpool8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, st>>>(p);
             else maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
             break;
