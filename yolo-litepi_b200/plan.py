@@ -328,18 +328,27 @@ def build_detector_plan(model: NcnnModel, in_size: int = 640) -> Plan:
     nc = head_specs[0][3][2].cout
     hc = 64 + (nc + 3) // 4 * 4
     # buffers for the branches first, the head buffer LAST (lp_detect_forward reads bufs.back())
+    # The first conv of the box branch and of the class branch read the same feature map with the same
+    # geometry: they run as ONE conv with concatenated output channels (one patch load, one launch, wider N).
     staged = []
     for feat, h, box, cls, row in head_specs:
-        hb1, hb2 = P.new_view(h, h, [box[0].cout]), P.new_view(h, h, [box[1].cout])
-        hc1, hc2 = P.new_view(h, h, [cls[0].cout]), P.new_view(h, h, [cls[1].cout])
-        staged.append((feat, box, cls, row, hb1, hb2, hc1, hc2))
+        first = P.new_view(h, h, [box[0].cout, cls[0].cout])
+        hb2, hc2 = P.new_view(h, h, [box[1].cout]), P.new_view(h, h, [cls[1].cout])
+        staged.append((feat, box, cls, row, first, hb2, hc2))
     head = P.buf(n_anchors, 1, hc, L.FMT_F32)
-    for feat, box, cls, row, hb1, hb2, hc1, hc2 in staged:
-        conv(box[0], feat, hb1)
-        conv(box[1], hb1, hb2)
+    for feat, box, cls, row, first, hb2, hc2 in staged:
+        b0, k0 = box[0], cls[0]
+        if b0.silu == k0.silu and b0.has_bias == k0.has_bias:
+            both = ConvRec(f"{b0.name}+{k0.name}", b0.cout + k0.cout, b0.cin, 3, 1, b0.pad, b0.has_bias, b0.silu,
+                           np.concatenate([b0.weight, k0.weight], 0),
+                           np.concatenate([b0.bias, k0.bias]) if b0.has_bias else None)
+            conv(both, feat, first)
+        else:
+            conv(b0, feat, first.seg(0))
+            conv(k0, feat, first.seg(1))
+        conv(box[1], first.seg(0), hb2)
         conv(box[2], hb2, View(head, (0,), (64,), False), row_off=row)
-        conv(cls[0], feat, hc1)
-        conv(cls[1], hc1, hc2)
+        conv(cls[1], first.seg(1), hc2)
         conv(cls[2], hc2, View(head, (64,), (nc,), False), row_off=row)
     dfl = next(it)
     if dfl.has_bias or dfl.cin != 16 or not np.array_equal(dfl.weight.ravel(), np.arange(16, dtype=np.float32)):
