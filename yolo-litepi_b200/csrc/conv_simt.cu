@@ -510,17 +510,18 @@ __global__ void resample_copy_kernel(ConvParams p) {
 // Vectorised split-f16 variants: one thread = one 16-byte chunk (8 channels) of one plane of one output
 // pixel; both the nearest-x2 upsample (stride 2) and the copy (stride 1) are bit-preserving.
 __global__ void resample_copy8_kernel(ConvParams p) {
-    const int cpp = p.cout >> 3;                                      // chunks per pixel
-    const long long total = 2LL * p.n_img * p.Ho * p.Wo * cpp;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // 32-bit index arithmetic (the host checks the item count fits): 64-bit divisions were most of this kernel
+    const unsigned cpp = (unsigned)p.cout >> 3;                       // chunks per pixel
+    const unsigned total = 2u * (unsigned)p.n_img * (unsigned)p.Ho * (unsigned)p.Wo * cpp;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int ch = (int)(i % cpp);
-    long long r = i / cpp;
-    const int ox = (int)(r % p.Wo); r /= p.Wo;
-    const int oy = (int)(r % p.Ho); r /= p.Ho;
-    const int img = (int)(r % p.n_img);
-    const int plane = (int)(r / p.n_img);
-    const int iy = oy / p.stride, ix = ox / p.stride;
+    const unsigned ch = i % cpp;
+    unsigned r = i / cpp;
+    const unsigned ox = r % (unsigned)p.Wo; r /= (unsigned)p.Wo;
+    const unsigned oy = r % (unsigned)p.Ho; r /= (unsigned)p.Ho;
+    const unsigned img = r % (unsigned)p.n_img;
+    const unsigned plane = r / (unsigned)p.n_img;
+    const unsigned iy = oy / (unsigned)p.stride, ix = ox / (unsigned)p.stride;
     const __half* s = (const __half*)p.in.base + (long long)plane * p.in.plane + (long long)img * p.in.img +
                       ((long long)iy * p.W + ix) * p.in.C + p.in.coff + ch * 8;
     __half* d = (__half*)p.out.base + (long long)plane * p.out.plane + (long long)img * p.out.img +
@@ -800,7 +801,7 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             p.stride = op.kind == LP_OP_UPSAMPLE2 ? 2 : 1;
             const bool v8 = p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16 && p.cout % 8 == 0 &&
                             p.in.coff % 8 == 0 && p.out.coff % 8 == 0 && p.out_cstride == 1 && p.seg_len == 0;
-            if (v8) resample_copy8_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(p);
+            if (v8 && total / 4 < (1ll << 31)) resample_copy8_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(p);
             else resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
             break;
         }
