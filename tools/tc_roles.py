@@ -37,4 +37,4 @@ for nm in names:
     print(f"[{o['ksize']}x{o['ksize']} s{o['stride']} {o['cin']}->{o['cout']}, {n_mma} MMA/tile, {d[6]/t/n_mma:.0f} cyc/MMA] ", end="")
     print(f"{nm:8s} tiles/CTA {t:3d} | loader/tile: wait_empty {d[0]/t:7.0f} issue {d[1]/t:7.0f} wait_cp {d[2]/t:7.0f} | "
           f"MMA/tile: wait_acc {d[3]/t:7.0f} wait_patch {d[4]/t:7.0f} wait_w {d[5]/t:7.0f} total {d[6]/t:7.0f} | "
-          f"epi/tile: wait {d[8]/t:6.0f} total {d[9]/t:6.0f} p1 {d[10]/t:6.0f} bar {d[11]/t:6.0f} p2 {d[12]/t:6.0f} tmem_ld {d[13]/t:6.0f} prologue {d[14]/t:6.0f}")
+          f"epi/tile: wait {d[8]/t:6.0f} total {d[9]/t:6.0f} p1 {d[10]/t:6.0f} stage_wait {d[11]/t:6.0f} prologue {d[14]/t:6.0f} | store/tile: wait {d[15]/t:6.0f} copy {d[12]/t:6.0f}")

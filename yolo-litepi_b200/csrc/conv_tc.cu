@@ -34,8 +34,9 @@
 
 namespace {
 
-constexpr int TC_THREADS = 576;
+constexpr int TC_THREADS = 704;
 constexpr int EPI_WARPS = 8, W_PRODUCER = 8, W_MMA = 9, W_LOADER0 = 10, LOADER_WARPS = 8;   // warp roles
+constexpr int W_STORE0 = 18, STORE_WARPS = 4, STORE_THREADS = STORE_WARPS * 32;             // staged tile -> global
 constexpr int LOADER_THREADS = LOADER_WARPS * 32;
 constexpr int MAX_PST = 8, MAX_AST = 4;    // patch / accumulator stages
 constexpr int TILE_M = 128;
@@ -66,6 +67,7 @@ struct TcParams {
     int n_mma, mtab_bytes;     // MMA issue table: one uint2 per tcgen05.mma of a tile
     int fills_per_tile;        // streaming weights: n_kb / w_stages (stage pattern repeats every tile)
     int epi_pitch, epi_bytes;  // epilogue staging: bytes per pixel row (+16 pad) and total (0 = direct stores)
+    int epi_bufs, epi_buf_bytes;   // staging buffers (2 = conversion and copy-out overlap, 1 = they alternate) and bytes of one
     int tab_bytes;             // 3x3: per-slot geometry table (py | px<<8) in shared memory
     int tmem_cols, acc_stride;  // TMEM columns allocated; column stride between the two accumulator stages
     unsigned magic_chunks, magic_pitch;   // ceil(2^32 / n) for division by n_chunks / pitch
@@ -194,7 +196,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     uint64_t* patch_empty = patch_full + MAX_PST;                // [MAX_PST]
     uint64_t* acc_full = patch_empty + MAX_PST;                  // [MAX_AST]
     uint64_t* acc_empty = acc_full + MAX_AST;                    // [MAX_AST]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + MAX_AST);
+    uint64_t* stage_full = acc_empty + MAX_AST;                  // [2] epilogue staging tile written
+    uint64_t* stage_empty = stage_full + 2;                      // [2] ... and copied out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + 2);
     uint8_t* patch0 = smem + 512;
     const int n_chunks = p.cin >> 3;
     const uint32_t plane_bytes = (uint32_t)n_chunks * p.slots_p * 16;
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         for (int s = 0; s < p.w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int s = 0; s < MAX_PST; ++s) { mbar_init(&patch_full[s], LOADER_THREADS); mbar_init(&patch_empty[s], 1); }
         for (int s = 0; s < MAX_AST; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS * 32); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&stage_full[s], EPI_WARPS * 32); mbar_init(&stage_empty[s], STORE_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) {
@@ -228,6 +233,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
 
     const bool pure = DFLAG(8);      // debugging: MMA warp alone, no barriers (measures the raw MMA rate)
     if (pure && warp != W_MMA) {
+    } else if (warp >= W_STORE0) {
+        // ================= store warps (128 threads) =================
+        // Copy each staged tile [plane][row][epi_pitch] to global memory with consecutive threads on consecutive
+        // 16-B pieces (whole pixel rows per warp store) while the epilogue warps already convert the next tile
+        // into the other staging buffer.  The loop is branch-free: the loads of four pieces are issued before the
+        // first (predicated) store, so one shared-memory latency is paid per four pieces, not per piece.
+        if (p.epi_bytes > 0) {
+            const int stt = threadIdx.x - W_STORE0 * 32;
+            const int esz = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 4;
+            const int n_planes = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 1;
+            const int cpr = (p.cout * esz) >> 4;                 // 16-B pieces per pixel row
+            const unsigned magic_cpr = (unsigned)((0x100000000ull + cpr - 1) / cpr);
+            const uint32_t epi_plane = (uint32_t)TILE_M * p.epi_pitch;
+            const int per_plane = TILE_M * cpr;
+            const int n_items = n_planes * per_plane;            // a multiple of 128 (TILE_M rows)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            uint32_t sb = 0, sb_phase = 0;
+            long long s_wait = 0, s_copy = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const uint8_t* stg = epi + (size_t)sb * p.epi_buf_bytes;
+                const long long* row_base = reinterpret_cast<const long long*>(stg + (size_t)n_planes * epi_plane);
+                const long long t0 = TCLK();
+                mbar_wait(&stage_full[sb], sb_phase);
+                const long long t1 = TCLK();
+                for (int q0 = stt; q0 < n_items; q0 += 4 * STORE_THREADS) {
+                    uint4 val[4];
+                    long long base[4];
+                    uint32_t off[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int q = q0 + u * STORE_THREADS;
+                        q = q < n_items ? q : stt;                 // clamp: the tail re-reads a valid piece and is not stored
+                        const int pl = q >= per_plane ? 1 : 0;
+                        const int qq = q - pl * per_plane;
+                        const int row = (int)__umulhi((unsigned)qq, magic_cpr);
+                        const int ch = qq - row * cpr;
+                        base[u] = row_base[row];
+                        val[u] = *reinterpret_cast<const uint4*>(stg + (uint32_t)pl * epi_plane + (uint32_t)row * (uint32_t)p.epi_pitch + ch * 16);
+                        off[u] = (uint32_t)ch * 16;
+                        if (pl) base[u] = base[u] < 0 ? base[u] : base[u] + p.out_plane;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (base[u] >= 0 && q0 + u * STORE_THREADS < n_items)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + base[u] * esz + off[u]) = val[u];
+                }
+                mbar_arrive(&stage_empty[sb]);                   // staging buffer free again
+                s_wait += t1 - t0; s_copy += TCLK() - t1;
+                if (++sb == (uint32_t)p.epi_bufs) { sb = 0; sb_phase ^= 1; }
+            }
+            if (DBG && p.dbg && blockIdx.x == 0 && stt == 0) { p.dbg[12] = s_copy; p.dbg[15] = s_wait; }
+        }
     } else if (warp >= W_LOADER0) {
         // ================= patch loaders (256 threads) =================
         // The loader's instruction stream is on the critical path of the small-channel layers, so the
@@ -464,14 +521,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         const int quad = warp & 3, half = warp >> 2;        // TMEM lane quadrant, column half
         const int c_split = (((p.cout >> 4) + 1) >> 1) << 4;   // 16-column groups: first ceil(n/2) to half 0, rest to half 1
         const int c_begin = half ? c_split : 0, c_end = half ? p.cout : c_split;
-        const int et = threadIdx.x;                          // 0..255
         const int esz = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 4;
         const int n_planes = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 1;
-        const int cpr = (p.cout * esz) >> 4;                 // 16-B chunks per pixel row
-        const unsigned magic_cpr = (unsigned)((0x100000000ull + cpr - 1) / cpr);
         const uint32_t epi_plane = (uint32_t)TILE_M * p.epi_pitch;
-        long long* row_base = reinterpret_cast<long long*>(epi + (size_t)n_planes * epi_plane);
         const bool staged = p.epi_bytes > 0;
+        uint32_t sb = 0, sb_phase = 0;                      // staging buffer of this tile
         asm volatile("griddepcontrol.wait;" ::: "memory");      // before any residual read / output write
         int it = 0;
         uint32_t as = 0, as_phase = 0;
@@ -502,7 +556,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             }
             const long long obase = (long long)oimg * p.out_img + (long long)opin * p.out_C + p.out_coff;
             const long long rbase = (long long)oimg * p.res_img + (long long)opin * p.res_C + p.res_coff;
-            if (staged && half == 0) row_base[r] = valid ? obase : -1;
+            uint8_t* stg = epi + (size_t)sb * p.epi_buf_bytes;
+            if (staged) {
+                const long long t0 = TCLK();
+                if (it >= p.epi_bufs) mbar_wait(&stage_empty[sb], sb_phase ^ 1);      // the store warps have drained it
+                e_bar += TCLK() - t0;
+                if (half == 0) reinterpret_cast<long long*>(stg + (size_t)n_planes * epi_plane)[r] = valid ? obase : -1;
+            }
             { long long t0 = TCLK();
               e_pre += t0 - e_top;
               mbar_wait(&acc_full[as], as_phase);
@@ -575,7 +635,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                             }
                         }
                     } else if (staged) {
-                        uint8_t* sp = epi + (size_t)r * p.epi_pitch + c0 * 2;
+                        uint8_t* sp = stg + (size_t)r * p.epi_pitch + c0 * 2;
                         *reinterpret_cast<uint4*>(sp) = oh[0];
                         *reinterpret_cast<uint4*>(sp + 16) = oh[1];
                         *reinterpret_cast<uint4*>(sp + epi_plane) = ol[0];
@@ -588,7 +648,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                         *reinterpret_cast<uint4*>(o + p.out_plane + 8) = ol[1];
                     }
                 } else if (staged) {
-                    uint8_t* sp = epi + (size_t)r * p.epi_pitch + c0 * 4;
+                    uint8_t* sp = stg + (size_t)r * p.epi_pitch + c0 * 4;
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         *reinterpret_cast<float4*>(sp + 16 * q) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
@@ -604,29 +664,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             if (++as == (uint32_t)p.acc_stages) { as = 0; as_phase ^= 1; }
             const long long tp2 = TCLK();
             e_p1 += tp2 - tp1;
-            if (staged && !DFLAG(2)) {
-                asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tile complete (epilogue warps only)
-                const long long tp3 = TCLK();
-                e_bar += tp3 - tp2;
-                const int per_plane = TILE_M * cpr;
-                for (int q = et; q < n_planes * per_plane; q += 256) {
-                    const int pl = q >= per_plane ? 1 : 0;
-                    const int qq = q - pl * per_plane;
-                    const int row = (int)__umulhi((unsigned)qq, magic_cpr);
-                    const int ch = qq - row * cpr;
-                    const long long base = row_base[row];
-                    if (base < 0) continue;
-                    const uint4 val = *reinterpret_cast<const uint4*>(epi + (size_t)pl * epi_plane + (size_t)row * p.epi_pitch + ch * 16);
-                    uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + ((base + (long long)pl * p.out_plane) * esz) + ch * 16;
-                    *reinterpret_cast<uint4*>(o) = val;
-                }
-                const long long tp4 = TCLK();
-                asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tile free for the next tile
-                e_p2 += tp4 - tp3;
-                e_bar += TCLK() - tp4;
+            if (staged) {
+                mbar_arrive(&stage_full[sb]);                    // release: the staged tile is visible to the store warps
+                if (++sb == (uint32_t)p.epi_bufs) { sb = 0; sb_phase ^= 1; }
             }
         }
-        if (DBG && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[12] = e_p2; p.dbg[13] = e_ld; p.dbg[14] = e_pre; }
+        if (DBG && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[13] = e_ld; p.dbg[14] = e_pre; (void)e_p2; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -730,9 +773,10 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     // Shared-memory plan.  Weights: resident if the whole layer fits beside >= 2 patch stages, else a ring
     // of 2-4 stages.  Epilogue staging
     // (coalesced stores) if >= 2 patch stages still fit.  Everything left goes to patch stages.
-    auto plan = [&](bool stage_epi) -> bool {
-        const size_t budget = total - (stage_epi ? epi_full : 0);
-        if (total < (stage_epi ? epi_full : 0)) return false;
+    auto plan = [&](int epi_bufs) -> bool {
+        const size_t epi_need = (size_t)epi_bufs * epi_full;
+        if (total < epi_need) return false;
+        const size_t budget = total - epi_need;
         if (w_all + 2 * patch_bytes <= budget && p.n_kb <= MAX_WST) { p.resident = 1; p.w_stages = p.n_kb; }
         else {
             p.resident = 0;
@@ -748,29 +792,38 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         int ps = (int)(left / patch_bytes);
         p.patch_stages = ps > MAX_PST ? MAX_PST : ps;
         if (p.patch_stages < 1) return false;
-        p.epi_bytes = stage_epi ? (int)epi_full : 0;
-        return !stage_epi || p.patch_stages >= 2;
+        p.epi_bufs = epi_bufs > 0 ? epi_bufs : 1;
+        p.epi_buf_bytes = (int)epi_full;
+        p.epi_bytes = (int)epi_need;
+        return epi_bufs == 0 || p.patch_stages >= 2;
     };
     // K-block size: the packed weights are [tap][8-channel chunk][plane][n][8], so any multiple of 16 that
-    // divides Cin is a valid block; take the largest whose ring fits
+    // divides Cin is a valid block; take the largest whose ring fits.  Staging: two buffers (conversion of
+    // tile i+1 overlaps the copy-out of tile i) if they fit, else one, else direct stores.  Streaming layers
+    // are MMA-bound: they prefer a larger weight block over the second staging buffer.
+    const int max_bufs = seg ? 0 : 2;
     bool ok = false;
     for (int d : {64, 48, 32, 16}) {
         if (op.cin % d) continue;
         p.kb_ch = d; p.n_cb = op.cin / d; p.n_units = taps * p.n_cb;
         p.unit_bytes = d * nb * 4;                                   // 2 planes x kb_ch x cout x 2 B
-        // units per weight block: resident -> as few blocks as barriers allow; streaming -> the largest block
-        // (fewest barrier round trips per tile) that still leaves two patch stages
         auto set_upb = [&](int upb) {
             p.upb = upb; p.n_kb = (p.n_units + upb - 1) / upb;
             p.stage_bytes = upb * p.unit_bytes;
         };
+        // resident weights: as few blocks as the barrier count allows
         set_upb((p.n_units + MAX_WST - 1) / MAX_WST);
-        if (((!seg && plan(true)) || plan(false)) && p.resident) { ok = true; break; }
-        for (int stage_epi = seg ? 0 : 1; stage_epi >= 0 && !ok; --stage_epi)
+        for (int bufs = max_bufs; bufs >= 0 && !ok; --bufs)
+            if (plan(bufs) && p.resident) ok = true;
+        for (int bufs = max_bufs > 1 ? 1 : max_bufs; bufs >= 0 && !ok; --bufs)
             for (int upb : {3, 2, 1}) {
                 if (upb > p.n_units) continue;
                 set_upb(upb);
-                if (plan(stage_epi != 0) && (upb == 1 || p.patch_stages >= 2)) { ok = true; break; }
+                if (plan(bufs) && (upb == 1 || p.patch_stages >= 2)) {
+                    if (bufs == 1 && max_bufs == 2 && plan(2) && (upb == 1 || p.patch_stages >= 2)) { ok = true; break; }   // second buffer for free
+                    plan(bufs);
+                    ok = true; break;
+                }
             }
         if (ok) break;
     }
