@@ -177,6 +177,16 @@ int lp_pack_records(lp_ctx* ctx, const int32_t* roi_src, const int32_t* frame_id
  * step is enqueued without a host synchronisation.  Null restores host counts. */
 int lp_set_roi_count_device(lp_ctx* ctx, const int32_t* n_rois_dev);
 
+/* ---- Evaluation matching.  Replaces section 1 of evaluate_predictions
+ * (e2e.py:687-731, box_iou :663-676): for every frame and every IoU threshold, each prediction keeps
+ * its best ground truth with iou >= t, each ground truth keeps the lowest-index prediction that chose
+ * it, and correct[p][t] = 1 iff their classes agree.  float64, numpy's operation order.
+ * pred_box [P][4] / gt_box [G][4] xyxy; *_off [n_frames + 1] prefix offsets; max_per_frame >=
+ * max over frames of (predictions + ground truths); correct [P][n_thr] u8.  All device pointers. */
+int lp_eval_match(lp_ctx* ctx, const double* pred_box, const int32_t* pred_cls, const int32_t* pred_off,
+                  const double* gt_box, const int32_t* gt_cls, const int32_t* gt_off, int n_frames,
+                  int max_per_frame, const double* thresholds, int n_thr, uint8_t* correct, void* stream);
+
 /* Workspace bytes lp_detect_forward / lp_classify need for the loaded plan (0 if not loaded). */
 size_t lp_workspace_bytes(lp_ctx* ctx, int net);
 

@@ -101,8 +101,68 @@ def main():
         c[fn + ".tensor_sum"] = np.array([float(t.astype(np.float64).sum()), float(np.abs(t).astype(np.float64).sum())])
         c[fn + ".tensor_row"] = t[:, 31, :].copy()
     np.savez_compressed(os.path.join(HERE, "classifier_input.npz"), **c)
-    for fn in ("detector_rand_seed0.npz", "detector_path.npz", "classifier_input.npz"):
+    make_eval_golden(ref)
+    for fn in ("detector_rand_seed0.npz", "detector_path.npz", "classifier_input.npz", "eval_cases.npz"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)) // 1024, "KiB")
+
+
+def eval_case(seed: int, n_img: int, n_cls: int, w: int = 1198, h: int = 681):
+    """Seeded evaluation workload: ground-truth signs per image, predictions = jittered copies (some with the
+    wrong class, some duplicated, some spurious), integer predicted boxes like HybridPipeline.run emits."""
+    rng = np.random.default_rng(seed)
+    preds, gts = [], []
+    for i in range(n_img):
+        ng = int(rng.integers(0, 7))
+        if i % 9 == 4:
+            ng = 0
+        g = []
+        for _ in range(ng):
+            bw, bh = rng.uniform(12, 120), rng.uniform(12, 120)
+            x1, y1 = rng.uniform(0, w - bw), rng.uniform(0, h - bh)
+            g.append([float(rng.integers(0, n_cls)), x1, y1, x1 + bw, y1 + bh])
+        pr = []
+        if i % 7 != 3:
+            for row in g:
+                for _ in range(int(rng.integers(0, 3))):                       # 0, 1 or 2 detections per sign
+                    j = rng.normal(0, 0.08, 4) * np.array([row[3] - row[1], row[4] - row[2]] * 2)
+                    bb = np.array(row[1:]) + j
+                    cls = int(row[0]) if rng.random() < 0.8 else int(rng.integers(0, n_cls))
+                    pr.append({"bbox": tuple(np.array(bb).astype(int)), "conf": float(rng.uniform(0.05, 1.0)), "cls_class": cls})
+            for _ in range(int(rng.integers(0, 3))):                               # false alarms
+                bw, bh = rng.uniform(12, 90), rng.uniform(12, 90)
+                x1, y1 = rng.uniform(0, w - bw), rng.uniform(0, h - bh)
+                pr.append({"bbox": tuple(np.array([x1, y1, x1 + bw, y1 + bh]).astype(int)), "conf": float(rng.uniform(0.05, 0.6)),
+                           "cls_class": int(rng.integers(0, n_cls))})
+        preds.append(pr); gts.append(g)
+    return preds, gts
+
+
+def pack_eval_case(preds, gts):
+    """Flat arrays (what the npz stores and tests rebuild the lists from)."""
+    pb = np.array([p["bbox"] for im in preds for p in im], np.int64).reshape(-1, 4)
+    pc = np.array([p["conf"] for im in preds for p in im], np.float64)
+    pk = np.array([p["cls_class"] for im in preds for p in im], np.int64)
+    pn = np.array([len(im) for im in preds], np.int64)
+    gb = np.array([r for im in gts for r in im], np.float64).reshape(-1, 5)
+    gn = np.array([len(im) for im in gts], np.int64)
+    return dict(pred_box=pb, pred_conf=pc, pred_cls=pk, pred_n=pn, gt=gb, gt_n=gn)
+
+
+def make_eval_golden(ref):
+    """evaluate_predictions (e2e.py:656-824) run UNMODIFIED on seeded cases; inputs and outputs recorded."""
+    import warnings
+    out = {}
+    for name, (seed, n_img, n_cls) in {"small": (0, 12, 3), "mid": (1, 80, 6), "wide": (2, 200, 49), "empty": (3, 0, 4)}.items():
+        preds, gts = eval_case(seed, n_img, n_cls)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = ref.evaluate_predictions(preds, gts, n_cls)
+        for k, v in pack_eval_case(preds, gts).items():
+            out[f"{name}.in.{k}"] = v
+        out[f"{name}.in.num_classes"] = np.array(n_cls)
+        for k, v in m.items():
+            out[f"{name}.out.{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "eval_cases.npz"), **out)
 
 
 if __name__ == "__main__":

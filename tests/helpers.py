@@ -59,3 +59,19 @@ def oracle_pipeline_run(det_oracle, clf_model, frame, conf, iou, min_area):
                     "det_class": int(classes[k]), "det_conf": float(scores[k]),
                     "cls_class": int(cls[j]), "cls_conf": float(np.max(probs[j]))})
     return res
+
+
+def load_eval_case(name: str):
+    """(all_preds, all_gts, num_classes, expected dict) of tests/golden/eval_cases.npz -- inputs and outputs of the
+    reference's evaluate_predictions recorded by tests/golden/make_golden.py."""
+    import numpy as np
+    d = np.load(os.path.join(GOLDEN, "eval_cases.npz"))
+    pn, gn = d[f"{name}.in.pred_n"], d[f"{name}.in.gt_n"]
+    pb, pc, pk, gb = d[f"{name}.in.pred_box"], d[f"{name}.in.pred_conf"], d[f"{name}.in.pred_cls"], d[f"{name}.in.gt"]
+    preds, gts, a, b = [], [], 0, 0
+    for i in range(len(pn)):
+        preds.append([{"bbox": tuple(pb[a + j]), "conf": float(pc[a + j]), "cls_class": int(pk[a + j])} for j in range(pn[i])])
+        gts.append([list(gb[b + j]) for j in range(gn[i])])
+        a += pn[i]; b += gn[i]
+    want = {k.split(".out.")[1]: d[k] for k in d.files if k.startswith(name + ".out.")}
+    return preds, gts, int(d[f"{name}.in.num_classes"]), want

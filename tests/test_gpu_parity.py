@@ -406,3 +406,72 @@ def test_config4_classifier_1024_crops(lp):
     # composition invariance: any sub-batch gives the same rows
     cls2, probs2 = c.predict_batch(crops[100:133])
     assert np.array_equal(cls2, cls[100:133]) and np.abs(probs2 - probs[100:133]).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ evaluation (8f.1)
+@pytest.mark.parametrize("case", ["small", "mid", "wide", "empty"])
+def test_eval_equals_reference_golden(lp, case):
+    """Evaluator.evaluate_predictions (GPU matching + host curves) against the recorded outputs of the reference's
+    evaluate_predictions: every key bit-exact (bool/int matching, float64 curves)."""
+    from helpers import load_eval_case
+    preds, gts, nc, want = load_eval_case(case)
+    got = lp.Evaluator().evaluate_predictions(preds, gts, nc)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert np.array_equal(np.asarray(got[k]), v), k
+
+
+def test_eval_match_vs_oracle_and_edges(lp):
+    from oracle import eval_ref as ER
+    ev = lp.Evaluator()
+    rng = np.random.default_rng(5)
+    # 300 frames, up to 60 predictions and 40 ground truths each, integer boxes on both sides (many exact overlaps)
+    pn = rng.integers(0, 61, 300); gn = rng.integers(0, 41, 300)
+    pn[7] = 0; gn[9] = 0; pn[11] = gn[11] = 0
+
+    def boxes(n):
+        xy = rng.integers(0, 600, (n, 2)); wh = rng.integers(8, 120, (n, 2))
+        return np.concatenate([xy, xy + wh], 1).astype(np.float64)
+    pb, gb = boxes(int(pn.sum())), boxes(int(gn.sum())) + rng.uniform(0, 0.5, (int(gn.sum()), 4))
+    pc, gc = rng.integers(0, 5, int(pn.sum())), rng.integers(0, 5, int(gn.sum()))
+    got = ev.match(pb, pc, pn, gb, gc, gn)
+    a = b = 0
+    for f in range(300):
+        want = ER.match_image_ref(pb[a:a + pn[f]], pc[a:a + pn[f]], gb[b:b + gn[f]], gc[b:b + gn[f]])
+        assert np.array_equal(got[a:a + pn[f]], want), f
+        a += pn[f]; b += gn[f]
+    assert got.any() and not got.all()
+    # identical boxes: iou = 1 - eps >= 0.95 at every threshold; the LOWEST-index duplicate prediction owns the ground truth
+    one = np.array([[10., 10., 50., 50.]])
+    c = ev.match(np.repeat(one, 3, 0), np.array([1, 1, 1]), np.array([3]), one, np.array([1]), np.array([1]))
+    assert c[0].all() and not c[1:].any()
+    # an exact IoU tie between two ground truths goes to the higher ground-truth index (documented tie rule)
+    g2 = np.array([[0., 0., 10., 10.], [20., 0., 30., 10.]])
+    c = ev.match(np.array([[5., 0., 25., 10.]]), np.array([2]), np.array([1]), g2, np.array([1, 2]), np.array([2]),
+                 thresholds=np.array([0.1]))
+    assert c[0, 0]
+    assert ev.match(np.zeros((0, 4)), np.zeros(0), np.array([0, 0]), one, np.array([1]), np.array([1, 0])).shape == (0, 10)
+
+
+def test_eval_of_pipeline_records(lp, v1_paths, clf):
+    """End to end: records of a batch evaluated against ground truth made from the pipeline's own output score
+    the maximum mAP50 = mAP50-95 on the classes present; dropping every second ground truth turns the unmatched
+    detections into false positives and lowers it."""
+    from litepi_b200 import synth
+    _, ref = clf
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, max_batch=16,
+                           classifier_state_dict=ref.state_dict(), seed=0)
+    frames = [synth.vn_frame(i) for i in range(16)]
+    fb = lp.detector.FrameBatch.from_host(frames, pipe.device)
+    rec = pipe.fetch_records(pipe.run_device(fb, 0.25, 0.45, 50))
+    res = pipe.records_to_results(rec, 16)
+    gts = [[[d["cls_class"], *[float(v) for v in d["bbox"]]] for d in r] for r in res]
+    ev = lp.Evaluator()
+    m = ev.evaluate_records(rec, 16, gts, 49)
+    # a perfect detector scores 0.995 under the reference's 101-point rule (the sentinel (recall 1, precision 0)
+    # costs half of the last 0.01-wide trapezoid)
+    assert m["mAP50"] == pytest.approx(0.995, abs=1e-9) and m["mAP50_95"] == pytest.approx(0.995, abs=1e-9)
+    assert m["fp"].sum() == 0 and m["fn"].sum() == 0 and m["tp"].sum() == rec.shape[0]
+    half = [g[::2] for g in gts]
+    m2 = ev.evaluate_records(rec, 16, half, 49)
+    assert m2["mAP50"] < 0.995 and m2["tp"].sum() <= sum(len(g) for g in half)

@@ -179,3 +179,25 @@ def test_gather_records_world2_gloo():
         assert p.exitcode == 0
     assert res[0] == res[1]
     assert [r[0] for r in res[0]] == [0, 2, 4] and len(res[0]) == 3
+
+
+def test_eval_host_metrics_equal_reference_golden():
+    """The product's host half of the evaluation (per-class curves, AP, best-F1: litepi_b200.evaluate.metrics_from_stats)
+    on a matching result computed by the oracle must reproduce the reference's recorded outputs bit for bit."""
+    from helpers import load_eval_case
+    from litepi_b200.evaluate import metrics_from_stats
+    from oracle import eval_ref as ER
+    for case in ("small", "mid", "wide"):
+        preds, gts, nc, want = load_eval_case(case)
+        cs, conf, pcs, tcs = [], [], [], []
+        for p, g in zip(preds, gts):
+            g = np.asarray(g, np.float64).reshape(-1, 5)
+            tcs.append(g[:, 0])
+            if not p:
+                continue
+            pb = np.array([q["bbox"] for q in p]); pc = np.array([q["cls_class"] for q in p])
+            cs.append(ER.match_image_ref(pb, pc, g[:, 1:], g[:, 0]))
+            conf.append(np.array([q["conf"] for q in p])); pcs.append(pc)
+        got = metrics_from_stats(np.concatenate(cs), np.concatenate(conf), np.concatenate(pcs), np.concatenate(tcs), nc)
+        for k, v in want.items():
+            assert np.array_equal(np.asarray(got[k]), v), (case, k)

@@ -165,3 +165,32 @@ def test_shufflenet_oracle_is_torchvision():
     b = PR.classify_lib(m, crops)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert PR.classify_ref(m, [])[0].shape == (0,)
+
+
+# ------------------------------------------------------------------ evaluation
+@pytest.mark.parametrize("case", ["small", "mid", "wide", "empty"])
+def test_eval_restatement_equals_reference_golden(case):
+    """oracle/eval_ref.py against outputs of the UNMODIFIED evaluate_predictions (e2e.py:656-824)."""
+    from helpers import load_eval_case
+    from oracle import eval_ref as ER
+    preds, gts, nc, want = load_eval_case(case)
+    got = ER.evaluate_predictions_ref(preds, gts, nc)
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert np.array_equal(np.asarray(got[k]), v), k
+
+
+def test_eval_restatement_equals_reference_live(ref_e2e):
+    """fresh seeds through the reference itself (only where /root/reference is mounted)"""
+    import warnings
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "golden"))
+    from make_golden import eval_case
+    from oracle import eval_ref as ER
+    for seed, n_img, nc in ((11, 30, 4), (12, 150, 58), (13, 5, 2)):
+        preds, gts = eval_case(seed, n_img, nc)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = ref_e2e.evaluate_predictions(preds, gts, nc)
+        got = ER.evaluate_predictions_ref(preds, gts, nc)
+        for k, v in want.items():
+            assert np.array_equal(np.asarray(got[k]), np.asarray(v)), (seed, k)

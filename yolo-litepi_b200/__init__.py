@@ -9,6 +9,7 @@ from .ncnn_model import load_ncnn  # noqa: F401
 from .detector import B200Detector  # noqa: F401
 from .classifier import B200Classifier  # noqa: F401
 from .pipeline import B200Pipeline, PipelineMetrics  # noqa: F401
+from .evaluate import Evaluator  # noqa: F401
 
 # reference-compatible aliases (src/vntsr/pipeline/e2e.py:195, :350, :399)
 NCNNDetector = B200Detector

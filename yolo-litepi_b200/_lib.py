@@ -66,6 +66,8 @@ _PROTOS = {
     "lp_pack_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lp_set_roi_count_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "lp_eval_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lp_launch_count": (C.c_int64, [C.c_void_p]),
     "lp_debug_tc_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lp_probe_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
