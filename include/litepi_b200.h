@@ -169,6 +169,13 @@ int lp_pack_records(lp_ctx* ctx, const int32_t* roi_src, const int32_t* frame_id
                     const int64_t* cls_argmax, const float* probs, int n_classes, int n_rois,
                     int32_t* records, void* stream);
 
+/* ROI semantics.  mode 0 (default) = src/vntsr/pipeline/e2e.py: clip x1,y1 to
+ * [0, w-1]/[0, h-1] and x2,y2 to [x1+1, w]/[y1+1, h] (:462-469), Pillow antialiased BILINEAR resize
+ * (:385-388).  mode 1 = src/tt100k/pipeline/e2e_optimize.py: clip all four to [0, w]/[0, h] (:480-483),
+ * keep iff area >= min_area and the box is non-empty (:486-496), cv2.resize INTER_LINEAR (:391-393).
+ * Affects lp_roi_select and lp_roi_resize of this context. */
+int lp_set_roi_mode(lp_ctx* ctx, int mode);
+
 /* Device-side ROI count.  The reference sizes its classifier batches on the host (len(rois),
  * e2e.py:477-485); a GPU pipeline would have to read the count back in the middle of a step and
  * leave the device idle meanwhile.  After this call with a non-null pointer (the int32 that

@@ -306,3 +306,26 @@ def classify_lib(model, rois_bgr: List[np.ndarray], size: int = 64):
         logits = model(batch)
         probs = torch.softmax(logits, dim=1).numpy()
     return np.argmax(probs, axis=1), probs, logits.numpy()
+
+
+# ------------------------------------------------------------------ e2e_optimize.py variant
+def roi_select_opt_ref(boxes: np.ndarray, shape, min_area: int):
+    """src/tt100k/pipeline/e2e_optimize.py:476-499: int32 truncation, clip to [0,w]x[0,h], area filter, and the
+    non-empty test of the ROI list comprehension.  Returns (rois [K,4] int32, indices of the kept detections)."""
+    h, w = shape[:2]
+    if len(boxes) == 0:
+        return np.zeros((0, 4), np.int32), []
+    b = np.asarray(boxes).astype(np.int32)
+    b[:, [0, 2]] = np.clip(b[:, [0, 2]], 0, w)
+    b[:, [1, 3]] = np.clip(b[:, [1, 3]], 0, h)
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    keep = (area >= min_area) & (b[:, 2] > b[:, 0]) & (b[:, 3] > b[:, 1])
+    return b[keep], [int(i) for i in np.nonzero(keep)[0]]
+
+
+def classifier_input_opt_ref(roi_bgr: np.ndarray, size: int = 64) -> np.ndarray:
+    """e2e_optimize.py:391-393: BGR->RGB then cv2.resize(INTER_LINEAR) (restated, no antialias) -> [size,size,3] u8."""
+    rgb = roi_bgr[:, :, ::-1]
+    if rgb.shape[0] == size and rgb.shape[1] == size:
+        return np.ascontiguousarray(rgb)
+    return cv_resize_linear_u8(np.ascontiguousarray(rgb), size, size)

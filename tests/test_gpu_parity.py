@@ -475,3 +475,37 @@ def test_eval_of_pipeline_records(lp, v1_paths, clf):
     half = [g[::2] for g in gts]
     m2 = ev.evaluate_records(rec, 16, half, 49)
     assert m2["mAP50"] < 0.995 and m2["tp"].sum() <= sum(len(g) for g in half)
+
+
+# ------------------------------------------------------------------------------------------ e2e_optimize.py mode (8f.3)
+def test_optimized_roi_mode(lp, v1_paths, clf):
+    """roi_mode="optimized": ROI integers and the cv2-INTER_LINEAR classifier input are bit-exact with the
+    restatement of e2e_optimize.py; the default mode is untouched."""
+    from litepi_b200 import synth
+    c, ref = clf
+    crops = synth.roi_crops(120, seed=9) + [np.random.default_rng(1).integers(0, 256, (64, 64, 3), dtype=np.uint8)]
+    c.set_preprocess("cv2")
+    try:
+        got = c.preprocess_batch(crops).cpu().numpy()
+    finally:
+        c.set_preprocess("pil")
+    want = np.stack([PR.classifier_input_opt_ref(cr) for cr in crops])
+    assert np.array_equal(got, want)
+    assert np.array_equal(c.preprocess_batch(crops[:8]).cpu().numpy(), np.stack([PR.classifier_input_ref(cr)[0] for cr in crops[:8]]))
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, max_batch=8,
+                           classifier_state_dict=ref.state_dict(), seed=0, roi_mode="optimized")
+    frames = [synth.vn_frame(i) for i in range(6)] + [synth.tt_frame(1)]
+    fb = lp.detector.FrameBatch.from_host(frames, pipe.device)
+    n = pipe.run_device(fb, 0.25, 0.45, 50)
+    rois = pipe.roi_xyxy[:n].cpu().numpy(); src = pipe.roi_src[:n].cpu().numpy()
+    dets = pipe.detector._collect(len(frames))
+    want_r, want_s, want_in = [], [], []
+    for i, f in enumerate(frames):
+        r, valid = PR.roi_select_opt_ref(dets[i][0], f.shape, 50)
+        want_r.extend(r.tolist()); want_s.extend([[i, k] for k in valid])
+        want_in.extend(PR.classifier_input_opt_ref(f[y1:y2, x1:x2]) for x1, y1, x2, y2 in r)
+    assert n == len(want_r) and n > 10
+    assert rois.tolist() == want_r and src.tolist() == want_s
+    assert np.array_equal(pipe.classifier.cls_in[:n].cpu().numpy(), np.stack(want_in))
+    with pytest.raises(ValueError):
+        lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, roi_mode="fast")

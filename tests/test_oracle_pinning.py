@@ -194,3 +194,33 @@ def test_eval_restatement_equals_reference_live(ref_e2e):
         got = ER.evaluate_predictions_ref(preds, gts, nc)
         for k, v in want.items():
             assert np.array_equal(np.asarray(got[k]), np.asarray(v)), (seed, k)
+
+
+# ------------------------------------------------------------------ e2e_optimize.py variant
+def test_optimized_variant_restatements():
+    """classifier_input_opt_ref against cv2 itself (what e2e_optimize.py:391-393 calls) on ROI-like shapes, and
+    roi_select_opt_ref against the reference's own numpy lines (:480-496) executed verbatim on the same boxes."""
+    rng = np.random.default_rng(3)
+    shapes = [(128, 128), (64, 64), (32, 32), (127, 129), (2, 2), (3, 200), (200, 3), (10, 90), (255, 31)] + \
+             [(int(rng.integers(2, 260)), int(rng.integers(2, 260))) for _ in range(60)]
+    for h, w in shapes:
+        roi = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = cv2.resize(cv2.cvtColor(roi, cv2.COLOR_BGR2RGB), (64, 64), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(PR.classifier_input_opt_ref(roi), want), (h, w)
+    for trial in range(50):
+        h, w = int(rng.integers(50, 2100)), int(rng.integers(50, 2100))
+        n = int(rng.integers(0, 40))
+        xy = rng.uniform(-30, max(h, w) + 30, (n, 2)); wh = rng.uniform(0, 200, (n, 2))
+        boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+        min_area = int(rng.choice([1, 50, 100]))
+        rois, valid = PR.roi_select_opt_ref(boxes, (h, w), min_area)
+        if n:
+            boxes_int = boxes.astype(np.int32)                                  # e2e_optimize.py:480-487
+            boxes_int[:, [0, 2]] = np.clip(boxes_int[:, [0, 2]], 0, w)
+            boxes_int[:, [1, 3]] = np.clip(boxes_int[:, [1, 3]], 0, h)
+            areas = (boxes_int[:, 2] - boxes_int[:, 0]) * (boxes_int[:, 3] - boxes_int[:, 1])
+            m = areas >= min_area
+            want = [tuple(b) for b in boxes_int[m] if b[2] > b[0] and b[3] > b[1]]
+            assert [tuple(r) for r in rois] == want
+        else:
+            assert len(rois) == 0 and valid == []

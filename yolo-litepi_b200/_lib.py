@@ -65,6 +65,7 @@ _PROTOS = {
                               C.c_void_p, C.c_void_p]),
     "lp_pack_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "lp_set_roi_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "lp_set_roi_count_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lp_eval_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

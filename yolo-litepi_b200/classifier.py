@@ -86,6 +86,12 @@ class B200Classifier:
         self._cap = 0
         self._alloc(self.max_batch)
 
+    def set_preprocess(self, mode: str):
+        """"pil" (e2e.py:385-388, default) or "cv2" (e2e_optimize.py:391-393) resize in preprocess_batch/predict_batch."""
+        if mode not in ("pil", "cv2"):
+            raise ValueError(f"Unknown preprocess mode: {mode}")
+        L.check(L.lib().lp_set_roi_mode(self.ctx.handle, 1 if mode == "cv2" else 0), "lp_set_roi_mode")
+
     def set_fused(self, enable: bool):
         L.check(L.lib().lp_set_fused_classifier(self.ctx.handle, 1 if enable else 0))
         self.fused = bool(enable) and self._has_fused

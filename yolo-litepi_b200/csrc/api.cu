@@ -165,6 +165,12 @@ extern "C" int lp_detect_forward(lp_ctx* ctx, const uint8_t* in, int batch, void
     return lp_launch_detect_tail(ctx, (const float*)((uint8_t*)workspace + hb.offset), batch, hb.c, out0, st);
 }
 
+extern "C" int lp_set_roi_mode(lp_ctx* ctx, int mode) {
+    LP_CHECK(ctx && (mode == 0 || mode == 1), "lp_set_roi_mode: mode must be 0 (e2e.py) or 1 (e2e_optimize.py)");
+    ctx->roi_mode = mode;
+    return 0;
+}
+
 extern "C" int lp_set_roi_count_device(lp_ctx* ctx, const int32_t* n_rois_dev) {
     LP_CHECK(ctx, "lp_set_roi_count_device: null context");
     ctx->roi_count_dev = n_rois_dev;

@@ -65,10 +65,26 @@ struct lp_ctx {
     int fused_slot = -1;             // index into the fused-classifier table (shufflenet_fused.cu)
     int use_fused = 1;
     int use_pdl = 1;                 // programmatic dependent launch between tensor-core conv kernels (env LP_NO_PDL=1 disables)
+    int roi_mode = 0;                // 0: e2e.py ROI rules + Pillow resize; 1: e2e_optimize.py rules + cv2 INTER_LINEAR
     const int* roi_count_dev = nullptr;   // lp_set_roi_count_device: ROI-side calls take their count from the device
     long long* tc_dbg = nullptr;     // device buffer (16 x int64) for conv_tc role timing; debugging only
 };
 #define LP_PROBE_RING 512
+
+// ---- OpenCV 8-bit INTER_LINEAR coefficient of output index d (11-bit fixed point; see preprocess.cu)
+__device__ __forceinline__ void lin_coef(int d, double scale, int n, bool clamp_coef, int& s, int& c0, int& c1) {
+    // explicit _rn ops: no FMA contraction, or the double result rounds differently from the CPU
+    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+    int si = (int)floorf(f);
+    f -= (float)si;
+    if (clamp_coef) {
+        if (si < 0) { si = 0; f = 0.f; }
+        if (si >= n - 1) { si = n - 1; f = 0.f; }
+    }
+    s = si;
+    c0 = (int)rintf(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    c1 = (int)rintf(__fmul_rn(f, 2048.f));
+}
 
 // ---- split-f16 helpers -------------------------------------------------------
 __device__ __forceinline__ float split_load(const __half* hi, const __half* lo, size_t i) {

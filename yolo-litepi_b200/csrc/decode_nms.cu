@@ -298,7 +298,7 @@ struct SizeTable {
 
 __global__ void __launch_bounds__(1024) roi_select_kernel(const float* __restrict__ boxes, const int* __restrict__ counts,
                                                           int max_det, SizeTable tab, int batch, int img_base,
-                                                          int min_area, int max_rois, int* __restrict__ roi_xyxy,
+                                                          int min_area, int max_rois, int mode, int* __restrict__ roi_xyxy,
                                                           int* __restrict__ roi_src, int* __restrict__ n_rois) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
@@ -323,8 +323,13 @@ __global__ void __launch_bounds__(1024) roi_select_kernel(const float* __restric
             const float* bx = boxes + ((long long)img * max_det + k) * 4;
             const int w = tab.w[img], h = tab.h[img];
             x1 = (int)bx[0]; y1 = (int)bx[1]; x2 = (int)bx[2]; y2 = (int)bx[3];   // trunc toward zero
-            x1 = min(max(x1, 0), w - 1); y1 = min(max(y1, 0), h - 1);
-            x2 = min(max(x2, x1 + 1), w); y2 = min(max(y2, y1 + 1), h);
+            if (mode == 0) {                            // e2e.py:462-469
+                x1 = min(max(x1, 0), w - 1); y1 = min(max(y1, 0), h - 1);
+                x2 = min(max(x2, x1 + 1), w); y2 = min(max(y2, y1 + 1), h);
+            } else {                                    // e2e_optimize.py:480-483: plain clip to the frame
+                x1 = min(max(x1, 0), w); x2 = min(max(x2, 0), w);
+                y1 = min(max(y1, 0), h); y2 = min(max(y2, 0), h);
+            }
             const long long area = (long long)(x2 - x1) * (y2 - y1);
             flag = (area >= (long long)min_area) && x2 > x1 && y2 > y1;
         }
@@ -367,7 +372,7 @@ extern "C" int lp_roi_select(lp_ctx* ctx, const float* boxes, const int32_t* cou
         SizeTable tab;
         for (int i = 0; i < n; ++i) { tab.h[i] = h_h[base + i]; tab.w[i] = w_h[base + i]; }
         roi_select_kernel<<<1, 1024, 0, st>>>(boxes + (size_t)base * max_det * 4, counts + base, max_det, tab, n, base,
-                                              min_area, max_rois, roi_xyxy, roi_src, n_rois);
+                                              min_area, max_rois, ctx->roi_mode, roi_xyxy, roi_src, n_rois);
         LP_LAUNCH_OK(ctx);
     }
     return 0;

@@ -21,20 +21,6 @@ struct FrameTable {
     int top[LP_MAX_TABLE];
 };
 
-__device__ __forceinline__ void lin_coef(int d, double scale, int n, bool clamp_coef, int& s, int& c0, int& c1) {
-    // explicit _rn ops: no FMA contraction, or the double result rounds differently from the CPU
-    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
-    int si = (int)floorf(f);
-    f -= (float)si;
-    if (clamp_coef) {
-        if (si < 0) { si = 0; f = 0.f; }
-        if (si >= n - 1) { si = n - 1; f = 0.f; }
-    }
-    s = si;
-    c0 = (int)rintf(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
-    c1 = (int)rintf(__fmul_rn(f, 2048.f));
-}
-
 // grid (S/4/blockDim.x.., S/ROWS, B); each thread produces 4 consecutive output pixels (12 bytes).
 template <int PX>
 __global__ void __launch_bounds__(160) letterbox_kernel(FrameTable tab, int S, uint8_t* __restrict__ out) {

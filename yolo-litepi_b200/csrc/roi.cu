@@ -128,6 +128,53 @@ __global__ void __launch_bounds__(256) roi_resize_kernel(RoiFrames fr, int img_b
     }
 }
 
+// e2e_optimize.py:391-393: cv2.cvtColor(BGR2RGB) + cv2.resize(INTER_LINEAR) of the ROI, bit-exact with OpenCV's
+// 11-bit fixed point (same arithmetic as the letterbox kernel).  Block per ROI; coefficients of the S columns
+// and S rows are tabulated in shared memory once, then each thread produces output pixels.
+__global__ void __launch_bounds__(256) roi_resize_linear_kernel(RoiFrames fr, int img_base, const int* __restrict__ roi_xyxy,
+                                                                const int* __restrict__ roi_src, int n_rois,
+                                                                const int* __restrict__ n_dev, int S, uint8_t* __restrict__ out) {
+    extern __shared__ int s_lin[];                      // [S][3] x: (sx, a0, a1) then [S][3] y: (sy, b0, b1)
+    const int r = blockIdx.x;
+    if (r >= n_rois || (n_dev && r >= *n_dev)) return;
+    const int img = roi_src[2 * r] - img_base;
+    if (img < 0 || img >= LP_MAX_TABLE) return;
+    const int x1 = roi_xyxy[4 * r], y1 = roi_xyxy[4 * r + 1], rw = roi_xyxy[4 * r + 2] - x1, rh = roi_xyxy[4 * r + 3] - y1;
+    const long long pitch = fr.pitch[img];
+    const uint8_t* __restrict__ src = fr.ptr[img] + (long long)y1 * pitch + (long long)x1 * 3;
+    uint8_t* dst = out + (long long)r * S * S * 3;
+    if (rw == S && rh == S) {                            // cv2.resize returns a copy when the size is unchanged
+        for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+            const int y = e / S, x = e - y * S;
+            const uint8_t* p = src + (long long)y * pitch + x * 3;
+            dst[e * 3 + 0] = p[2]; dst[e * 3 + 1] = p[1]; dst[e * 3 + 2] = p[0];
+        }
+        return;
+    }
+    const double scale_x = 1.0 / ((double)S / (double)rw), scale_y = 1.0 / ((double)S / (double)rh);
+    for (int t = threadIdx.x; t < 2 * S; t += blockDim.x) {
+        int s0, c0, c1;
+        if (t < S) lin_coef(t, scale_x, rw, true, s0, c0, c1);
+        else lin_coef(t - S, scale_y, rh, false, s0, c0, c1);
+        s_lin[t * 3] = s0; s_lin[t * 3 + 1] = c0; s_lin[t * 3 + 2] = c1;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+        const int y = e / S, x = e - y * S;
+        const int sx = s_lin[x * 3], a0 = s_lin[x * 3 + 1], a1 = s_lin[x * 3 + 2];
+        const int sy = s_lin[(S + y) * 3], b0 = s_lin[(S + y) * 3 + 1], b1 = s_lin[(S + y) * 3 + 2];
+        const int sx1 = min(sx + 1, rw - 1);
+        const int y0 = min(max(sy, 0), rh - 1), yy1 = min(max(sy + 1, 0), rh - 1);
+        const uint8_t *r0 = src + (long long)y0 * pitch, *r1 = src + (long long)yy1 * pitch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int t0 = (int)__ldg(r0 + sx * 3 + c) * a0 + (int)__ldg(r0 + sx1 * 3 + c) * a1;
+            const int t1 = (int)__ldg(r1 + sx * 3 + c) * a0 + (int)__ldg(r1 + sx1 * 3 + c) * a1;
+            dst[e * 3 + (2 - c)] = (uint8_t)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
+        }
+    }
+}
+
 extern "C" size_t lp_roi_resize_scratch_bytes(int, int, int) { return 0; }   // coefficients live in shared memory
 
 extern "C" int lp_roi_resize(lp_ctx* ctx, const uint8_t* const* frames_h, const int64_t* pitch_h, int batch,
@@ -137,6 +184,18 @@ extern "C" int lp_roi_resize(lp_ctx* ctx, const uint8_t* const* frames_h, const 
     LP_CHECK(out_size > 0 && out_size <= 128 && max_side > 0, "lp_roi_resize: bad out_size/max_side");
     if (n_rois <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->roi_mode == 1) {
+        for (int base = 0; base < batch; base += LP_MAX_TABLE) {
+            const int n = batch - base < LP_MAX_TABLE ? batch - base : LP_MAX_TABLE;
+            RoiFrames fr;
+            for (int i = 0; i < n; ++i) { fr.ptr[i] = frames_h[base + i]; fr.pitch[i] = pitch_h[base + i]; }
+            for (int i = n; i < LP_MAX_TABLE; ++i) { fr.ptr[i] = nullptr; fr.pitch[i] = 0; }
+            roi_resize_linear_kernel<<<n_rois, 256, (size_t)out_size * 6 * sizeof(int), st>>>(fr, base, roi_xyxy, roi_src, n_rois,
+                                                                                            ctx->roi_count_dev, out_size, out);
+            LP_LAUNCH_OK(ctx);
+        }
+        return 0;
+    }
     const double sc = (double)max_side / out_size;
     const int kmax = (int)ceil(sc < 1.0 ? 1.0 : sc) * 2 + 1;
     int tmp_rows = 3 * kmax > 96 ? 3 * kmax : 96;

@@ -51,7 +51,8 @@ class B200Pipeline:
                  cls_input_size: int = 64, use_gpu_detector: bool = False, detector_threads: int = 4,
                  classifier_device: str = "cpu", batch_size: int = 8,
                  device: int = 0, max_batch: int = 64, max_det: int = 1024, max_rois: Optional[int] = None,
-                 classifier_state_dict: Optional[dict] = None, seed: Optional[int] = None):
+                 classifier_state_dict: Optional[dict] = None, seed: Optional[int] = None,
+                 roi_mode: str = "reference"):
         self.detector = B200Detector(detector_param, detector_bin, input_size=det_input_size,
                                      use_gpu=use_gpu_detector, num_threads=detector_threads,
                                      device=device, max_batch=max_batch, max_det=max_det, seed=seed or 0)
@@ -61,6 +62,13 @@ class B200Pipeline:
                                          input_size=cls_input_size, device=classifier_device,
                                          state_dict=classifier_state_dict, cuda_device=device, seed=seed,
                                          max_batch=min(max(256, 16 * int(max_batch)), 1024))
+        # ROI semantics: "reference" = src/vntsr/pipeline/e2e.py (clip rules :462-469, Pillow resize); "optimized" =
+        # src/tt100k/pipeline/e2e_optimize.py (plain clip :480-483, cv2 INTER_LINEAR resize :391-393)
+        if roi_mode not in ("reference", "optimized"):
+            raise ValueError(f"Unknown roi_mode: {roi_mode}")
+        self.roi_mode = roi_mode
+        for ctx in (self.detector.ctx, self.classifier.ctx):
+            L.check(L.lib().lp_set_roi_mode(ctx.handle, 1 if roi_mode == "optimized" else 0), "lp_set_roi_mode")
         self.batch_size = batch_size          # reference's classifier mini-batch; ROIs are classified in one pass here
         self.device = self.detector.device
         self.ctx = self.detector.ctx
