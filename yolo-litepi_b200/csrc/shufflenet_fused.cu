@@ -88,9 +88,9 @@ __device__ __forceinline__ void f_bulk_g2s_multicast(void* dst, const void* src,
 }
 
 // rows of W that fit one weight stage
-__device__ __forceinline__ int chunk_rows(int cin, int cout) {
+__device__ __forceinline__ int chunk_rows(int cin, int cout, int slot_floats) {
     const int cout_p = (cout + 3) & ~3;
-    const int r = WBUF_FLOATS / cout_p;
+    const int r = slot_floats / cout_p;
     return r < cin ? r : cin;
 }
 
@@ -103,7 +103,8 @@ __device__ __forceinline__ int chunk_rows(int cin, int cout) {
 template <int RT>
 __device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C, float* __restrict__ out, int out_C, int dst_cs,
                                          int rows, int cin, int cout, const float* __restrict__ bias, int relu, int ks_log2,
-                                         const float* __restrict__ wbuf, uint64_t* full, uint64_t* empty, uint32_t& chunk_ctr) {
+                                         const float* __restrict__ wbuf, int slot_floats, uint64_t* full, uint64_t* empty,
+                                         uint32_t& chunk_ctr) {
     const int cout_p = (cout + 3) & ~3;
     const int ncg = cout_p >> 2, nrg = (rows + RT - 1) / RT;
     const int n_tiles = nrg * ncg;
@@ -118,13 +119,13 @@ __device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C,
     int roff[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) roff[r] = min(r0 + r, rows - 1) * in_C;
-    const int R = chunk_rows(cin, cout);
+    const int R = chunk_rows(cin, cout, slot_floats);
     for (int k0 = 0; k0 < cin; k0 += R, ++chunk_ctr) {
         const int nr = min(R, cin - k0);
         const uint32_t slot = chunk_ctr & 1;
         f_mbar_wait(&full[slot], (chunk_ctr >> 1) & 1);
         if (active) {
-            const float* wp = wbuf + slot * WBUF_FLOATS + c0;
+            const float* wp = wbuf + slot * slot_floats + c0;
             const float* ap = in + k0;
 #pragma unroll 2
             for (int ci = ks; ci < nr; ci += KS) {
@@ -172,19 +173,26 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 1)
 shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const int* __restrict__ n_dev, const float* __restrict__ W,
                         const FStep* __restrict__ steps, int n_front, int n_back, int G, int in_hw,
                         float mean, float stdv, float* __restrict__ logits, int n_classes, int wbuf_off,
-                        long long* dbg, int cs) {
+                        int back_off, int back_floats, long long* dbg, int cs) {
     extern __shared__ __align__(16) float sm[];
     __shared__ FStep s_steps[FUSED_MAX_STEPS];
     __shared__ float s_norm[256];
     __shared__ uint64_t s_full[2], s_empty[2], s_cready[2];   // weights landed / consumed (local) / every CTA armed (leader)
+    __shared__ uint64_t s_phase;                              // the compute threads finished a pass (front end of a ROI / back end)
     const int tid = threadIdx.x;
+    // Weight stages.  Front end: two 24-KB stages behind the activations.  Back end: the front end's buffers are
+    // dead, so the two stages grow over them ([back_off, back_off + 2*back_floats)): the stream is bound by the
+    // bytes in flight per SM, and 2 x 61 KB in flight instead of 2 x 24 KB is what the larger stages buy.  The
+    // regions overlap, so the producer starts a pass only after the compute threads finished the previous one.
     float* wbuf = sm + wbuf_off;                            // [2][WBUF_FLOATS]
+    float* wbig = sm + back_off;                            // [2][back_floats]
     for (int i = tid; i < (n_front + n_back) * (int)(sizeof(FStep) / 4); i += FUSED_BLOCK)
         reinterpret_cast<int*>(s_steps)[i] = reinterpret_cast<const int*>(steps)[i];
     if (tid == 0) {
         f_mbar_init(&s_full[0], 1); f_mbar_init(&s_full[1], 1);
         f_mbar_init(&s_empty[0], FUSED_THREADS); f_mbar_init(&s_empty[1], FUSED_THREADS);
         f_mbar_init(&s_cready[0], cs); f_mbar_init(&s_cready[1], cs);
+        f_mbar_init(&s_phase, FUSED_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ToTensor + Normalize exactly as torchvision computes them: (u8 / 255 - mean) / std, IEEE divisions
@@ -207,16 +215,19 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
         if (tid == FUSED_THREADS) {
             const uint32_t rank = f_cluster_rank();
             const uint16_t mask = (uint16_t)((1u << cs) - 1u);
-            uint32_t ctr = 0;
+            uint32_t ctr = 0, passes = 0;
             for (int iter = 0; iter < n_iters; ++iter) {
-                for (int pass = 0; pass <= G; ++pass) {
+                for (int pass = 0; pass <= G; ++pass, ++passes) {
                     const bool back = (pass == G);
                     const int s_begin = back ? n_front : 0, s_end = back ? n_front + n_back : n_front;
+                    if (passes) f_mbar_wait(&s_phase, (passes - 1) & 1);      // previous pass done: its buffers and stages are free
+                    float* wdst = back ? wbig : wbuf;
+                    const int slot_floats = back ? back_floats : WBUF_FLOATS;
                     for (int si = s_begin; si < s_end; ++si) {
                         const FStep& st = s_steps[si];
                         if (st.op != FS_PW) continue;
                         const int cout_p = (st.cout + 3) & ~3;
-                        const int R = chunk_rows(st.cin, st.cout);
+                        const int R = chunk_rows(st.cin, st.cout, slot_floats);
                         for (int k0 = 0; k0 < st.cin; k0 += R, ++ctr) {
                             const int nr = min(R, st.cin - k0);
                             const uint32_t slot = ctr & 1;
@@ -226,7 +237,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                             f_mbar_arrive_remote(&s_cready[slot], 0);
                             if (rank == 0) {
                                 f_mbar_wait_cluster(&s_cready[slot], (ctr >> 1) & 1);
-                                f_bulk_g2s_multicast(wbuf + slot * WBUF_FLOATS, W + st.w_off + (size_t)k0 * cout_p, bytes, &s_full[slot], mask);
+                                f_bulk_g2s_multicast(wdst + slot * slot_floats, W + st.w_off + (size_t)k0 * cout_p, bytes, &s_full[slot], mask);
                             }
                         }
                     }
@@ -322,7 +333,8 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     const int tiles = ((rows + rt - 1) / rt) * ncg;
                     int ksl = 0;
                     while (ksl < 3 && (tiles << (ksl + 1)) <= FUSED_THREADS) ++ksl;
-#define PW_CALL(RT_) pw_layer<RT_>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, bias, st.relu, ksl, wbuf, s_full, s_empty, chunk_ctr)
+#define PW_CALL(RT_) pw_layer<RT_>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, bias, st.relu, ksl, back ? wbig : wbuf, \
+                                   back ? back_floats : WBUF_FLOATS, s_full, s_empty, chunk_ctr)
                     if (rt == 8) PW_CALL(8);
                     else if (rt == 4) PW_CALL(4);
                     else if (rt == 2) PW_CALL(2);
@@ -424,6 +436,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                 CSYNC();
                 if (dbg && blockIdx.x == 0 && tid == 0) dbg[si] += clock64() - t_step;
             }
+            f_mbar_arrive(&s_phase);          // pass finished: the producer may start the next pass's weight stream
         }
     }
     }   // compute threads
@@ -436,6 +449,7 @@ struct lp_fused_cls {
     int n_front = 0, n_back = 0, G = 0, in_hw = 0, n_classes = 0;
     size_t smem_bytes = 0;
     int wbuf_off = 0;
+    int back_off = 0, back_floats = 0;   // back-end weight stages (floats): start and size of one
     int cluster = 1;            // CTAs sharing one multicast weight stream (env LP_CLS_CLUSTER; measured: 2 = no gain, the
                                 // stream is bound by bytes in flight per SM, not by L2; 4+ halves the resident CTAs)
     float mean = 0.f, stdv = 1.f;
@@ -444,7 +458,8 @@ struct lp_fused_cls {
 static lp_fused_cls g_fused[16];       // one slot per context id (contexts are few and long-lived)
 
 extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_back, const float* weights,
-                                        int group, int in_hw, int n_classes, size_t smem_bytes, float mean, float stdv) {
+                                        int group, int in_hw, int n_classes, size_t smem_bytes, size_t back_bytes,
+                                        float mean, float stdv) {
     LP_CHECK(ctx && steps_dev && weights, "lp_fused_classifier_load: null argument");
     LP_CHECK(n_front + n_back <= FUSED_MAX_STEPS && n_front > 0 && n_back > 0, "lp_fused_classifier_load: bad step counts");
     LP_CHECK(smem_bytes <= 227 * 1024, "lp_fused_classifier_load: %zu B shared memory exceeds 227 KB", smem_bytes);
@@ -455,8 +470,20 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
     // the host-built map covers the activations; the two weight stages are appended here
     f.wbuf_off = (int)((smem_bytes + 15) / 16 * 4);
     f.smem_bytes = (size_t)f.wbuf_off * 4 + 2 * WBUF_FLOATS * 4;
+    // back-end stages: everything between the end of the back end's activations and the end of the allocation,
+    // which is grown to 224 KB (one CTA per SM anyway)
+    LP_CHECK(back_bytes > 0 && back_bytes <= smem_bytes, "lp_fused_classifier_load: bad back-end extent");
+    {
+        cudaFuncAttributes fa{};
+        LP_CUDA(cudaFuncGetAttributes(&fa, shufflenet_fused_kernel));
+        const size_t dyn_max = ((size_t)227 * 1024 - fa.sharedSizeBytes) & ~(size_t)1023;     // static tables share the 227 KB
+        LP_CHECK(f.smem_bytes <= dyn_max, "lp_fused_classifier_load: %zu B dynamic shared memory do not fit", f.smem_bytes);
+        f.smem_bytes = dyn_max;
+    }
+    f.back_off = (int)((back_bytes + 15) / 16 * 4);
+    f.back_floats = (int)(((f.smem_bytes / 4 - f.back_off) / 2) & ~(size_t)3);
+    if (f.back_floats < WBUF_FLOATS) { f.back_off = f.wbuf_off; f.back_floats = WBUF_FLOATS; }
     smem_bytes = f.smem_bytes;
-    LP_CHECK(smem_bytes <= 218 * 1024, "lp_fused_classifier_load: group %d needs %zu B shared memory", group, smem_bytes);
     LP_CUDA(cudaFuncSetAttribute(shufflenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     { const char* e = getenv("LP_CLS_CLUSTER"); f.cluster = e ? atoi(e) : 1; if (f.cluster < 1 || f.cluster > 8) f.cluster = 1; }
     f.loaded = true;
@@ -479,7 +506,7 @@ int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cuda
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, ctx->roi_count_dev, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
-                                        f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, ctx->tc_dbg, cs);
+                                        f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, f.back_off, f.back_floats, ctx->tc_dbg, cs);
     if (le != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(le)); return -2; }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

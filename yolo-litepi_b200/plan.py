@@ -496,7 +496,8 @@ FSTEP_WORDS = 18        # struct FStep in csrc/shufflenet_fused.cu
 
 def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
     """Step list + fp32 weight blob for the persistent fused ShuffleNetV2 kernel
-    (csrc/shufflenet_fused.cu).  Returns (steps int32 [n, 18], weights f32, n_front, n_back, smem_bytes).
+    (csrc/shufflenet_fused.cu).  Returns (steps int32 [n, 18], weights f32, n_front, n_back, smem_bytes,
+    back_bytes = extent of the map the back end still uses).
 
     Shared-memory map (floats): Y = G x 7424 (stage tensor A) | scratch.  Back end: B = G x 7424,
     T1 = G x 7424, T2 = G x 3712.  Front end (per ROI) overlays the scratch: u8 crop, conv1 output,
@@ -619,4 +620,5 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
     n_back = len(steps) - n_front
     arr = np.asarray(steps, dtype=np.int32)
     assert arr.shape[1] == FSTEP_WORDS
-    return arr, np.concatenate(blobs), n_front, n_back, total_floats * 4
+    back_floats = S + G * (2 * ymax + t2_roi)                        # Y | B | T1 | T2: all the back end touches
+    return arr, np.concatenate(blobs), n_front, n_back, total_floats * 4, back_floats * 4
