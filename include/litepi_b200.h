@@ -109,11 +109,13 @@ int lp_set_tensor_core(lp_ctx* ctx, int enable);
  * host-built step list (plan.py build_fused_classifier; struct FStep in csrc/shufflenet_fused.cu, 18 x int32
  * per step, device memory) over an fp32 weight blob.  When loaded, lp_classify uses it instead of the
  * layer-by-layer plan; lp_set_fused_classifier(ctx, 0) switches back.  smem_bytes = extent of the activation
- * map, back_bytes = extent the back end (steps n_front..) still uses: the shared memory behind it holds the
- * back end's weight stages. */
+ * map, back_bytes = extent the back end (steps n_front..) still uses; behind it the shared memory holds
+ * astage_bytes of fp16 activation staging and the back end's weight stages.  weights16 (device, may be NULL) =
+ * split-f16 weights [cout_p8][hi|lo][L] of the back end's pointwise layers (FStep.w16_off), which then run on
+ * the tensor cores (mma.sync, Ahi*Bhi + Alo*Bhi + Ahi*Blo in fp32). */
 int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_back, const float* weights,
-                             int group, int in_hw, int n_classes, size_t smem_bytes, size_t back_bytes,
-                             float mean, float stdv);
+                             const void* weights16, int group, int in_hw, int n_classes, size_t smem_bytes,
+                             size_t back_bytes, size_t astage_bytes, float mean, float stdv);
 int lp_set_fused_classifier(lp_ctx* ctx, int enable);
 
 /* ---- K1: letterbox.  Replaces letterbox() + cvtColor (e2e.py:66-86, :224-225).

@@ -76,13 +76,16 @@ class B200Classifier:
         # layer-by-layer plan above stays loaded as the cross-check (set_fused(False))
         self.fused = self._has_fused = bool(fused) and self.input_size == 64
         if self.fused:
-            steps, fw, n_front, n_back, smem, back = build_fused_classifier(sd, group=fused_group, in_size=self.input_size)
+            steps, fw, n_front, n_back, smem, back, w16, astage = build_fused_classifier(sd, group=fused_group,
+                                                                                          in_size=self.input_size)
             with torch.cuda.device(self.device):
                 self.fused_steps = torch.from_numpy(steps).to(self.device)
                 self.fused_weights = torch.from_numpy(fw).to(self.device)
+                self.fused_weights16 = torch.from_numpy(w16.view(np.int16)).to(self.device)
             L.check(L.lib().lp_fused_classifier_load(self.ctx.handle, _ptr(self.fused_steps), n_front, n_back,
-                                                     _ptr(self.fused_weights), fused_group, self.input_size,
-                                                     self.num_classes, smem, back, 0.18, 0.34), "lp_fused_classifier_load")
+                                                     _ptr(self.fused_weights), _ptr(self.fused_weights16), fused_group,
+                                                     self.input_size, self.num_classes, smem, back, astage, 0.18, 0.34),
+                    "lp_fused_classifier_load")
         self._cap = 0
         self._alloc(self.max_batch)
 

@@ -28,7 +28,7 @@ struct FStep {
     int relu;
     int w_off, b_off;          // float offsets into the weight blob
     int dst_roi_stride;        // front end: added per ROI index to dst (0 otherwise)
-    int pad0;
+    int w16_off;               // > 0: split-f16 weights of this pointwise layer in the fp16 blob, in units of 16 B (+1); 0: none
 };
 
 constexpr int FUSED_THREADS = 512;            // compute threads; one more warp streams weights
@@ -85,6 +85,104 @@ __device__ __forceinline__ void f_mbar_wait_cluster(uint64_t* bar, uint32_t pari
 __device__ __forceinline__ void f_bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
                  ::"r"(f_smem_u32(dst)), "l"(src), "r"(bytes), "r"(f_smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// ---- tensor-core pointwise layers (back end) --------------------------------------------------------------
+// fp16 weight rows are [cout_p8][plane hi|lo][L] halves with L = cin_p16 + pad, L == 4 (mod 32): the stride
+// between output channels is L 32-bit words, so the 8 channels x 4 k-pairs a warp reads for a B fragment hit
+// 32 different banks.
+__device__ __forceinline__ int w16_row_halves(int cin) {
+    const int cin_p = (cin + 15) & ~15;
+    return cin_p + ((4 - cin_p) & 31);
+}
+// output channels per weight stage (multiple of 8)
+__device__ __forceinline__ int chunk_couts(int cin, int cout, int slot_floats) {
+    const int cout_p = (cout + 7) & ~7;
+    const int n = ((slot_floats * 4) / (w16_row_halves(cin) * 4)) & ~7;
+    return n < cout_p ? n : cout_p;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(f_smem_u32(p)));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Pointwise conv on the tensor cores (legacy warp-level mma.sync: the tiles are 16 x 8, far below a tcgen05
+// tile).  fp32 parity comes from the same split as the detector: x = hi + lo in fp16, and
+// Ahi*Bhi + Alo*Bhi + Ahi*Blo accumulated in fp32.  Step 1: all threads convert the fp32 activations
+// [rows][cin] to two fp16 planes [rows_p16][cin_p16 + 8] (row stride == 4 words mod 32: conflict-free
+// ldmatrix).  Step 2: weights arrive in chunks of output channels (every chunk holds complete K), a warp owns
+// 16x8 output tiles.  Step 3: bias/ReLU and the channel-shuffle store pattern straight from the fragments.
+__device__ __forceinline__ void pw_layer_mma(const float* __restrict__ in, int in_C, float* __restrict__ out, int out_C, int dst_cs,
+                                             int rows, int cin, int cout, const float* __restrict__ bias, int relu,
+                                             __half* __restrict__ astage, const float* __restrict__ wbuf, int slot_floats,
+                                             uint64_t* full, uint64_t* empty, uint32_t& chunk_ctr) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rows_p = (rows + 15) & ~15, cin_p = (cin + 15) & ~15, cout_p = (cout + 7) & ~7;
+    const int LA = cin_p + 8, L = w16_row_halves(cin);
+    __half* Ah = astage;
+    __half* Al = astage + rows_p * LA;
+    for (int e = tid; e < rows_p * (cin_p >> 1); e += FUSED_THREADS) {
+        const int r = e / (cin_p >> 1), c = (e - r * (cin_p >> 1)) * 2;
+        float x0 = 0.f, x1 = 0.f;
+        if (r < rows) {
+            if (c < cin) x0 = in[r * in_C + c];
+            if (c + 1 < cin) x1 = in[r * in_C + c + 1];
+        }
+        const __half2 hi = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(hi);
+        *reinterpret_cast<__half2*>(Ah + r * LA + c) = hi;
+        *reinterpret_cast<__half2*>(Al + r * LA + c) = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    }
+    CSYNC();
+    const int m_tiles = rows_p >> 4, ksteps = cin_p >> 4;
+    const int NN = chunk_couts(cin, cout, slot_floats);
+    for (int n0 = 0; n0 < cout_p; n0 += NN, ++chunk_ctr) {
+        const int nn = min(NN, cout_p - n0);
+        const uint32_t slot = chunk_ctr & 1;
+        f_mbar_wait(&full[slot], (chunk_ctr >> 1) & 1);
+        const __half* Wc = reinterpret_cast<const __half*>(wbuf + slot * slot_floats);      // [nn][2][L]
+        const int n_tiles = nn >> 3;
+        for (int item = warp; item < m_tiles * n_tiles; item += FUSED_THREADS / 32) {
+            const int mt = item / n_tiles, nt = item - mt * n_tiles;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const __half* arow_h = Ah + (mt * 16 + (lane & 15)) * LA + (lane >> 4) * 8;
+            const __half* arow_l = arow_h + rows_p * LA;
+            const __half* brow = Wc + (size_t)(nt * 8 + (lane >> 2)) * 2 * L + (lane & 3) * 2;
+#pragma unroll 2
+            for (int ks = 0; ks < ksteps; ++ks) {
+                uint32_t ah[4], al[4];
+                ldmatrix_x4(ah, arow_h + ks * 16);
+                ldmatrix_x4(al, arow_l + ks * 16);
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(brow + ks * 16);
+                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(brow + ks * 16 + 8);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(brow + L + ks * 16);
+                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(brow + L + ks * 16 + 8);
+                mma_f16(acc, ah, bh0, bh1);
+                mma_f16(acc, al, bh0, bh1);
+                mma_f16(acc, ah, bl0, bl1);
+            }
+            const int c = n0 + nt * 8 + (lane & 3) * 2;
+            const int r0 = mt * 16 + (lane >> 2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = r0 + 8 * h;
+                if (r >= rows) continue;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (c + j < cout) {
+                        const float v = acc[2 * h + j] + __ldg(bias + c + j);
+                        out[(size_t)r * out_C + (c + j) * dst_cs] = relu ? fmaxf(v, 0.f) : v;
+                    }
+                }
+            }
+        }
+        f_mbar_arrive(&empty[slot]);              // 512 arrivals free the stage for the producer
+    }
 }
 
 // rows of W that fit one weight stage
@@ -171,6 +269,7 @@ __device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C,
 
 __global__ void __launch_bounds__(FUSED_BLOCK, 1)
 shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const int* __restrict__ n_dev, const float* __restrict__ W,
+                        const uint4* __restrict__ W16, int astage_off,
                         const FStep* __restrict__ steps, int n_front, int n_back, int G, int in_hw,
                         float mean, float stdv, float* __restrict__ logits, int n_classes, int wbuf_off,
                         int back_off, int back_floats, long long* dbg, int cs) {
@@ -226,6 +325,26 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     for (int si = s_begin; si < s_end; ++si) {
                         const FStep& st = s_steps[si];
                         if (st.op != FS_PW) continue;
+                        if (back && st.w16_off > 0) {
+                            // tensor-core layer: chunks of output channels, rows of 2 planes x L halves (4*L bytes)
+                            const int NN = chunk_couts(st.cin, st.cout, slot_floats), cout_p8 = (st.cout + 7) & ~7;
+                            const int row_b = w16_row_halves(st.cin) * 4;
+                            for (int n0 = 0; n0 < cout_p8; n0 += NN, ++ctr) {
+                                const int nn = min(NN, cout_p8 - n0);
+                                const uint32_t slot = ctr & 1;
+                                if (ctr >= 2) f_mbar_wait(&s_empty[slot], ((ctr >> 1) - 1) & 1);
+                                const uint32_t bytes = (uint32_t)nn * row_b;
+                                f_mbar_expect_tx(&s_full[slot], bytes);
+                                f_mbar_arrive_remote(&s_cready[slot], 0);
+                                if (rank == 0) {
+                                    f_mbar_wait_cluster(&s_cready[slot], (ctr >> 1) & 1);
+                                    f_bulk_g2s_multicast(wdst + slot * slot_floats,
+                                                         reinterpret_cast<const uint8_t*>(W16 + (st.w16_off - 1)) + (size_t)n0 * row_b,
+                                                         bytes, &s_full[slot], mask);
+                                }
+                            }
+                            continue;
+                        }
                         const int cout_p = (st.cout + 3) & ~3;
                         const int R = chunk_rows(st.cin, st.cout, slot_floats);
                         for (int k0 = 0; k0 < st.cin; k0 += R, ++ctr) {
@@ -325,6 +444,11 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     const int rows = rois * st.H * st.W;
                     const float* ip = src + st.src_off;
                     float* op = dst + st.dst_off;
+                    if (back && st.w16_off > 0) {
+                        pw_layer_mma(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.b_off, st.relu,
+                                     reinterpret_cast<__half*>(sm + astage_off), wbig, back_floats, s_full, s_empty, chunk_ctr);
+                        break;
+                    }
                     // RT = min(8, rows) rows per thread; K split over the largest power of two <= 8 that keeps
                     // tiles * KS within the 512 compute threads (plan.py guarantees tiles <= 512)
                     const int ncg = (st.cout + 3) >> 2;
@@ -446,6 +570,8 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
 struct lp_fused_cls {
     const FStep* steps_dev = nullptr;
     const float* weights = nullptr;
+    const uint4* weights16 = nullptr;   // split-f16 pointwise weights of the back end (may be null: SIMT pointwise layers)
+    int astage_off = 0;                 // float offset of the fp16 activation staging of the tensor-core pointwise layers
     int n_front = 0, n_back = 0, G = 0, in_hw = 0, n_classes = 0;
     size_t smem_bytes = 0;
     int wbuf_off = 0;
@@ -458,14 +584,15 @@ struct lp_fused_cls {
 static lp_fused_cls g_fused[16];       // one slot per context id (contexts are few and long-lived)
 
 extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_back, const float* weights,
-                                        int group, int in_hw, int n_classes, size_t smem_bytes, size_t back_bytes,
-                                        float mean, float stdv) {
+                                        const void* weights16, int group, int in_hw, int n_classes, size_t smem_bytes,
+                                        size_t back_bytes, size_t astage_bytes, float mean, float stdv) {
     LP_CHECK(ctx && steps_dev && weights, "lp_fused_classifier_load: null argument");
     LP_CHECK(n_front + n_back <= FUSED_MAX_STEPS && n_front > 0 && n_back > 0, "lp_fused_classifier_load: bad step counts");
     LP_CHECK(smem_bytes <= 227 * 1024, "lp_fused_classifier_load: %zu B shared memory exceeds 227 KB", smem_bytes);
     LP_CHECK(ctx->fused_slot >= 0 && ctx->fused_slot < 16, "lp_fused_classifier_load: too many contexts");
     lp_fused_cls& f = g_fused[ctx->fused_slot];
-    f.steps_dev = (const FStep*)steps_dev; f.weights = weights; f.n_front = n_front; f.n_back = n_back;
+    f.steps_dev = (const FStep*)steps_dev; f.weights = weights; f.weights16 = (const uint4*)weights16;
+    f.n_front = n_front; f.n_back = n_back;
     f.G = group; f.in_hw = in_hw; f.n_classes = n_classes; f.mean = mean; f.stdv = stdv;
     // the host-built map covers the activations; the two weight stages are appended here
     f.wbuf_off = (int)((smem_bytes + 15) / 16 * 4);
@@ -480,9 +607,11 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
         LP_CHECK(f.smem_bytes <= dyn_max, "lp_fused_classifier_load: %zu B dynamic shared memory do not fit", f.smem_bytes);
         f.smem_bytes = dyn_max;
     }
-    f.back_off = (int)((back_bytes + 15) / 16 * 4);
+    // [back end activations | fp16 activation staging of the tensor-core pointwise layers | stage 0 | stage 1]
+    f.astage_off = (int)((back_bytes + 15) / 16 * 4);
+    f.back_off = f.astage_off + (int)((astage_bytes + 15) / 16 * 4);
+    LP_CHECK((size_t)f.back_off * 4 + 2 * WBUF_FLOATS * 4 <= f.smem_bytes, "lp_fused_classifier_load: no room for the back-end weight stages");
     f.back_floats = (int)(((f.smem_bytes / 4 - f.back_off) / 2) & ~(size_t)3);
-    if (f.back_floats < WBUF_FLOATS) { f.back_off = f.wbuf_off; f.back_floats = WBUF_FLOATS; }
     smem_bytes = f.smem_bytes;
     LP_CUDA(cudaFuncSetAttribute(shufflenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     { const char* e = getenv("LP_CLS_CLUSTER"); f.cluster = e ? atoi(e) : 1; if (f.cluster < 1 || f.cluster > 8) f.cluster = 1; }
@@ -505,7 +634,7 @@ int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cuda
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, ctx->roi_count_dev, f.weights, f.steps_dev, f.n_front, f.n_back, f.G,
+    cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, ctx->roi_count_dev, f.weights, f.weights16, f.astage_off, f.steps_dev, f.n_front, f.n_back, f.G,
                                         f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, f.back_off, f.back_floats, ctx->tc_dbg, cs);
     if (le != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(le)); return -2; }
     ctx->launches++;

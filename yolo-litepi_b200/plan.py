@@ -497,7 +497,8 @@ FSTEP_WORDS = 18        # struct FStep in csrc/shufflenet_fused.cu
 def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
     """Step list + fp32 weight blob for the persistent fused ShuffleNetV2 kernel
     (csrc/shufflenet_fused.cu).  Returns (steps int32 [n, 18], weights f32, n_front, n_back, smem_bytes,
-    back_bytes = extent of the map the back end still uses).
+    back_bytes = extent of the map the back end still uses, weights16 = split-f16 pointwise weights for the
+    tensor-core layers, astage_bytes = their fp16 activation staging).
 
     Shared-memory map (floats): Y = G x 7424 (stage tensor A) | scratch.  Back end: B = G x 7424,
     T1 = G x 7424, T2 = G x 3712.  Front end (per ROI) overlays the scratch: u8 crop, conv1 output,
@@ -519,12 +520,33 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
             blobs.append(np.zeros(pad, np.float32)); nf[0] += pad
         return off
 
+    h16: List[np.ndarray] = []
+    nh = [0]
+    last16 = [0]
+
     def pw_w(conv, bn):
         w, b = _fold_bn(sd[conv + ".weight"], sd, bn)                # [cout, cin, 1, 1]
         cout, cin = w.shape[:2]
         cp = (cout + 3) // 4 * 4
         wp = np.zeros((cin, cp), np.float32); wp[:, :cout] = w.reshape(cout, cin).T
         bp = np.zeros(cp, np.float32); bp[:cout] = b
+        # tensor-core copy: [cout_p8][hi|lo][L] fp16, L = cin_p16 + pad with L == 4 (mod 32) (csrc w16_row_halves)
+        last16[0] = 0
+        if cin <= 256:                                                # conv5 (464 -> 1024) stays on the fp32 stream
+            cin_p = (cin + 15) // 16 * 16
+            L = cin_p + ((4 - cin_p) % 32)
+            w2 = w.reshape(cout, cin).astype(np.float32)
+            hi = w2.astype(np.float16)
+            lo = (w2 - hi.astype(np.float32)).astype(np.float16)
+            blk = np.zeros(((cout + 7) // 8 * 8, 2, L), np.float16)
+            blk[:cout, 0, :cin] = hi
+            blk[:cout, 1, :cin] = lo
+            assert nh[0] % 8 == 0
+            last16[0] = nh[0] // 8 + 1                                # units of 16 B, +1 so that 0 means "none"
+            h16.append(blk.ravel()); nh[0] += blk.size
+            pad = (-nh[0]) % 8
+            if pad:
+                h16.append(np.zeros(pad, np.float16)); nh[0] += pad
         return push(wp), push(bp), cin, cout
 
     def dw_w(conv, bn):
@@ -537,7 +559,8 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
     def step(op, src, dst, src_C=0, src_off=0, dst_C=0, dst_off=0, dst_cs=1, cin=0, cout=0, H=0, W=0, stride=1, relu=0,
              w_off=0, b_off=0, roi_stride=0):
         steps.append([op, src, dst, src_C, src_off, dst_C, dst_off, dst_cs, cin, cout, H, W, stride, relu, w_off, b_off,
-                      roi_stride, 0])
+                      roi_stride, last16[0] if op == FS_PW else 0])
+        last16[0] = 0
 
     c1 = sd["conv1.0.weight"].shape[0]                                # 24
     widths = [sd[f"stage{s}.0.branch2.5.weight"].shape[0] for s in (2, 3, 4)]   # 58, 116, 232
@@ -621,4 +644,11 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
     arr = np.asarray(steps, dtype=np.int32)
     assert arr.shape[1] == FSTEP_WORDS
     back_floats = S + G * (2 * ymax + t2_roi)                        # Y | B | T1 | T2: all the back end touches
-    return arr, np.concatenate(blobs), n_front, n_back, total_floats * 4, back_floats * 4
+    # fp16 activation staging of the tensor-core pointwise layers: two planes [rows_p16][cin_p16 + 8]
+    astage = 0
+    for st in steps[n_front:]:
+        if st[0] == FS_PW and st[17] > 0:
+            rows_p = (G * st[10] * st[11] + 15) // 16 * 16
+            astage = max(astage, 2 * rows_p * ((st[8] + 15) // 16 * 16 + 8) * 2)
+    w16 = np.concatenate(h16) if h16 else np.zeros(8, np.float16)
+    return arr, np.concatenate(blobs), n_front, n_back, total_floats * 4, back_floats * 4, w16, astage
