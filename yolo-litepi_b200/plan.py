@@ -532,7 +532,7 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
         bp = np.zeros(cp, np.float32); bp[:cout] = b
         # tensor-core copy: [cout_p8][hi|lo][L] fp16, L = cin_p16 + pad with L == 4 (mod 32) (csrc w16_row_halves)
         last16[0] = 0
-        if cin <= 256:                                                # conv5 (464 -> 1024) stays on the fp32 stream
+        if cin <= 128:                  # stage 4 (232) and conv5 (464) are bound by the weight stream: they stay on the fp32 path
             cin_p = (cin + 15) // 16 * 16
             L = cin_p + ((4 - cin_p) % 32)
             w2 = w.reshape(cout, cin).astype(np.float32)
