@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         // 16-B pieces (whole pixel rows per warp store) while the epilogue warps already convert the next tile
         // into the other staging buffer.  The loop is branch-free: the loads of four pieces are issued before the
         // first (predicated) store, so one shared-memory latency is paid per four pieces, not per piece.
-        if (p.epi_bytes > 0) {
+        if (p.epi_bytes > 0 && p.epi_bufs == 2) {          // with one staging buffer the epilogue warps copy it out themselves
             const int stt = threadIdx.x - W_STORE0 * 32;
             const int esz = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 4;
             const int n_planes = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 1;
@@ -525,6 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         const int n_planes = p.out_fmt == LP_FMT_SPLIT16 ? 2 : 1;
         const uint32_t epi_plane = (uint32_t)TILE_M * p.epi_pitch;
         const bool staged = p.epi_bytes > 0;
+        const bool handoff = p.epi_bufs == 2;               // two staging buffers: dedicated store warps copy them out
         uint32_t sb = 0, sb_phase = 0;                      // staging buffer of this tile
         asm volatile("griddepcontrol.wait;" ::: "memory");      // before any residual read / output write
         int it = 0;
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             uint8_t* stg = epi + (size_t)sb * p.epi_buf_bytes;
             if (staged) {
                 const long long t0 = TCLK();
-                if (it >= p.epi_bufs) mbar_wait(&stage_empty[sb], sb_phase ^ 1);      // the store warps have drained it
+                if (handoff && it >= p.epi_bufs) mbar_wait(&stage_empty[sb], sb_phase ^ 1);      // the store warps have drained it
                 e_bar += TCLK() - t0;
                 if (half == 0) reinterpret_cast<long long*>(stg + (size_t)n_planes * epi_plane)[r] = valid ? obase : -1;
             }
@@ -664,12 +665,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             if (++as == (uint32_t)p.acc_stages) { as = 0; as_phase ^= 1; }
             const long long tp2 = TCLK();
             e_p1 += tp2 - tp1;
-            if (staged) {
+            if (staged && handoff) {
                 mbar_arrive(&stage_full[sb]);                    // release: the staged tile is visible to the store warps
                 if (++sb == (uint32_t)p.epi_bufs) { sb = 0; sb_phase ^= 1; }
+            } else if (staged) {
+                // single staging buffer (the MMA-bound streaming layers): all 256 epilogue threads copy the tile out,
+                // consecutive threads on consecutive 16-B pieces
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const long long tp3 = TCLK();
+                const int cpr = (p.cout * esz) >> 4;
+                const unsigned magic_cpr = (unsigned)((0x100000000ull + cpr - 1) / cpr);
+                const int per_plane = TILE_M * cpr;
+                const long long* row_base = reinterpret_cast<const long long*>(stg + (size_t)n_planes * epi_plane);
+                for (int q = threadIdx.x; q < n_planes * per_plane; q += 256) {
+                    const int pl = q >= per_plane ? 1 : 0;
+                    const int qq = q - pl * per_plane;
+                    const int row = (int)__umulhi((unsigned)qq, magic_cpr);
+                    const int ch = qq - row * cpr;
+                    const long long base = row_base[row];
+                    if (base < 0) continue;
+                    const uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)pl * epi_plane + (size_t)row * p.epi_pitch + ch * 16);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + ((base + (long long)pl * p.out_plane) * esz) + ch * 16) = val;
+                }
+                e_p2 += TCLK() - tp3;
+                asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tile free for the next tile
             }
         }
-        if (DBG && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[13] = e_ld; p.dbg[14] = e_pre; (void)e_p2; }
+        if (DBG && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { p.dbg[8] = e_wait; p.dbg[9] = TCLK() - e_total0; p.dbg[10] = e_p1; p.dbg[11] = e_bar; p.dbg[13] = e_ld; p.dbg[14] = e_pre; if (!handoff) p.dbg[12] = e_p2; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
