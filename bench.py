@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--lanes", type=int, default=2, help="batches in flight per GPU (pipeline instances on their own CUDA streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
                     help="device-resident steps only (no e2e / latency / CPU legs): the command ncu wraps")
@@ -208,17 +209,23 @@ def main():
     B = args.batch
     param, binp = model_paths("vntsr")
     clf_sd = PR.build_shufflenet(NUM_CLASSES, seed=0).state_dict()
-    pipe = litepi_b200.B200Pipeline(param, binp, None, "shufflenetv2", num_classes=NUM_CLASSES, device=local_rank,
-                                    max_batch=B, classifier_state_dict=clf_sd, seed=0)
+    # Two pipeline instances on two CUDA streams: consecutive batches are independent, so batch k+1 starts while the
+    # tail of batch k (partially filled last waves of its persistent kernels) still runs.  Each owns its workspace.
+    n_lanes = max(1, args.lanes)
+    pipes = [litepi_b200.B200Pipeline(param, binp, None, "shufflenetv2", num_classes=NUM_CLASSES, device=local_rank,
+                                      max_batch=B, classifier_state_dict=clf_sd, seed=0) for _ in range(n_lanes)]
+    lanes = [torch.cuda.Stream(device=torch.device("cuda", local_rank)) for _ in range(n_lanes)]
+    pipe = pipes[0]
     # rank r owns frames i with i % world == r  (frame ids are global)
     ids = [rank + world * i for i in range(B)]
     frames = np.stack([synth.vn_frame(i) for i in ids])
     host = torch.from_numpy(frames).pin_memory()
-    dev_frames = [torch.empty_like(host, device=dev) for _ in range(2)]
-    dev_frames[0].copy_(host)
+    dev_frames = [torch.empty_like(host, device=dev) for _ in range(n_lanes)]
+    for d in dev_frames:
+        d.copy_(host)
     frame_ids = torch.tensor(ids, dtype=torch.int32, device=dev)
-    fb0 = FrameBatch.from_device(dev_frames[0])
-    fbs = [fb0, FrameBatch.from_device(dev_frames[1])]
+    fbs = [FrameBatch.from_device(d) for d in dev_frames]
+    fb0 = fbs[0]
 
     def barrier():
         if world > 1:
@@ -234,27 +241,37 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()                                     # nvidia-smi needs a few hundred ms to produce its first line
     for _ in range(args.warmup):
-        pipe.run_device(fb0, CONF, IOU, MIN_AREA, frame_ids)
+        for ln in range(n_lanes):
+            pipes[ln].run_device(fbs[ln], CONF, IOU, MIN_AREA, frame_ids)
     barrier()
-    pipe.ctx.probe_set(L.NET_DETECTOR, dom)
     t_spin = time.time()
     while len(sampler.lines) == 0 and time.time() - t_spin < 3.0:
         time.sleep(0.05)
     sampler.mark()
-    launches0 = pipe.counters.launch_count()
+    launches0 = sum(p_.counters.launch_count() for p_ in pipes)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_rois = 0
     rec_ring = torch.empty((args.steps,) + tuple(pipe.records.shape), dtype=torch.int32, device=dev)
     cnt_ring = torch.zeros((args.steps,), dtype=torch.int32, device=dev)
     barrier()
-    e0.record()
-    # steps are enqueued back to back: the ROI count stays on the device (lp_set_roi_count_device), so a step
-    # needs no host round trip; each step's records and count are kept on the device for the final gather
+    main = torch.cuda.current_stream()
+    e0.record(main)
+    for st_ in lanes:
+        st_.wait_event(e0)
+    # steps are enqueued back to back, alternating between the lanes: the ROI count stays on the device
+    # (lp_set_roi_count_device), so a step needs no host round trip; each step's records and count are kept on the
+    # device for the final gather
     for k in range(args.steps):
-        pipe.enqueue_device(fb0, CONF, IOU, MIN_AREA, frame_ids)
-        rec_ring[k].copy_(pipe.records, non_blocking=True)          # preallocated: no allocator call (= no implicit sync) in the timed region
-        cnt_ring[k:k + 1].copy_(pipe.n_rois, non_blocking=True)
-    pipe.finish(fb0, frame_ids)                          # waits; validates capacities of the last step
+        ln = k % n_lanes
+        with torch.cuda.stream(lanes[ln]):
+            pipes[ln].enqueue_device(fbs[ln], CONF, IOU, MIN_AREA, frame_ids)
+            rec_ring[k].copy_(pipes[ln].records, non_blocking=True)      # preallocated: no allocator call (= no implicit sync) in the timed region
+            cnt_ring[k:k + 1].copy_(pipes[ln].n_rois, non_blocking=True)
+    for st_ in lanes:
+        main.wait_stream(st_)
+    for ln in range(n_lanes):
+        with torch.cuda.stream(lanes[ln]):
+            pipes[ln].finish(fbs[ln], frame_ids)         # waits; validates capacities of the lane's last step
     counts_h = cnt_ring.cpu().tolist()
     if counts_h and max(counts_h) > pipe.max_rois:
         raise RuntimeError("bench: a step exceeded max_rois")
@@ -265,10 +282,8 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = pipe.counters.launch_count() - launches0
+    launches = sum(p_.counters.launch_count() for p_ in pipes) - launches0
     clocks = sampler.stop()
-    probe = pipe.ctx.probe_read()
-    pipe.ctx.probe_set(L.NET_DETECTOR, -1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -283,38 +298,34 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---------------- end-to-end with host frames (e2e): double-buffered pinned H2D + D2H of records
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    # ---------------- roofline of the dominant kernel: a single-lane pass of the same steps with CUDA events around every launch of
+    # that kernel on its stream (with several batches in flight the kernels of different batches share the SMs, which
+    # stretches any one launch and says nothing about the kernel)
+    pipe.ctx.probe_set(L.NET_DETECTOR, dom)
+    for _ in range(args.steps):
+        pipe.enqueue_device(fb0, CONF, IOU, MIN_AREA, frame_ids)
+    pipe.finish(fb0, frame_ids)
+    probe = pipe.ctx.probe_read()
+    pipe.ctx.probe_set(L.NET_DETECTOR, -1)
 
+    # ---------------- end-to-end with host frames (e2e): pinned H2D + hot path + D2H of records
+    # Each lane does its own H2D -> hot path -> D2H on its stream; the lanes overlap each other (copies of one batch
+    # under the kernels of the other), and the host reads step s - n_lanes back while step s runs.
     n_out = [0]
 
     def e2e_loop(steps):
         d2h = 0
-        main_stream = torch.cuda.current_stream()
-        with torch.cuda.stream(copy_stream):
-            dev_frames[0].copy_(host, non_blocking=True)
-            ready[0].record(copy_stream)
-        for s in range(steps):
-            cur, nxt = s % 2, (s + 1) % 2
-            if s + 1 < steps:
-                with torch.cuda.stream(copy_stream):
-                    if s >= 1:
-                        copy_stream.wait_event(consumed[nxt])
-                    dev_frames[nxt].copy_(host, non_blocking=True)
-                    ready[nxt].record(copy_stream)
-            main_stream.wait_event(ready[cur])
-            pipe.enqueue_device(fbs[cur], CONF, IOU, MIN_AREA, frame_ids, slot=cur)
-            consumed[cur].record(main_stream)
-            pipe.enqueue_fetch(cur)                      # D2H of the step's records, queued behind the step
-            if s >= 1:
-                rec = pipe.collect(nxt)                  # read step s-1 back while step s runs
-                n_out[0] += rec.shape[0]
+        for s_ in range(steps):
+            ln = s_ % n_lanes
+            if s_ >= n_lanes:
+                n_out[0] += pipes[ln].collect(0).shape[0]
+            with torch.cuda.stream(lanes[ln]):
+                dev_frames[ln].copy_(host, non_blocking=True)
+                pipes[ln].enqueue_device(fbs[ln], CONF, IOU, MIN_AREA, frame_ids, slot=0)
+                pipes[ln].enqueue_fetch(0)               # D2H of the step's records, queued behind the step
             d2h += pipe.records.numel() * 4 + 4 + 4 * B
-        if steps:
-            rec = pipe.collect((steps - 1) % 2)
-            n_out[0] += rec.shape[0]
+        for ln in range(min(n_lanes, steps)):
+            n_out[0] += pipes[ln].collect(0).shape[0]
         return d2h
 
     e2e_loop(args.warmup)
@@ -361,7 +372,7 @@ def main():
                    "weights": "reference trained v1 (model.ncnn.bin)" if binp else "random-init (weights not staged)",
                    "classifier_weights": "random-init seed 0 (reference ships none)",
                    "l2": "per-step inputs (157 MB frames) + 2.2 GB activation workspace exceed the 126 MB L2",
-                   "rois_per_step": n_rois / max(args.steps, 1), "parallelism": f"frames sharded over {world} GPU(s)"},
+                   "rois_per_step": n_rois / max(args.steps, 1), "parallelism": f"frames sharded over {world} GPU(s); {n_lanes} batches in flight per GPU (CUDA streams)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(host.numel()),
                 "d2h_bytes_per_step": int(d2h_total / max(args.steps, 1)), "ms_per_step": ms_e / args.steps},
@@ -371,6 +382,7 @@ def main():
                      "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "traffic_unit": "bytes per launch (ncu dram read+write, profiles/dominant_kernel_traffic.json)",
                      "peak_source": pk_src + " bf16_tflops_sustained", "launch_ms": dom_ms,
+                     "measured_in": "single-lane pass of the same steps, CUDA events around each launch on its stream",
                      "flops_per_launch": dom_flops},
     }
     if not args.no_cpu_baseline:

@@ -34,9 +34,9 @@
 
 namespace {
 
-constexpr int TC_THREADS = 704;
-constexpr int EPI_WARPS = 8, W_PRODUCER = 8, W_MMA = 9, W_LOADER0 = 10, LOADER_WARPS = 8;   // warp roles
-constexpr int W_STORE0 = 18, STORE_WARPS = 4, STORE_THREADS = STORE_WARPS * 32;             // staged tile -> global
+constexpr int TC_THREADS = 640;             // 20 warps = 5 per SM sub-partition: 96 registers per thread (22 warps would cap them at 80)
+constexpr int EPI_WARPS = 8, W_PRODUCER = 8, W_MMA = 9, W_LOADER0 = 10, LOADER_WARPS = 6;   // warp roles
+constexpr int W_STORE0 = 16, STORE_WARPS = 4, STORE_THREADS = STORE_WARPS * 32;             // staged tile -> global
 constexpr int LOADER_THREADS = LOADER_WARPS * 32;
 constexpr int MAX_PST = 8, MAX_AST = 4;    // patch / accumulator stages
 constexpr int TILE_M = 128;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
             if (DBG && p.dbg && blockIdx.x == 0 && stt == 0) { p.dbg[12] = s_copy; p.dbg[15] = s_wait; }
         }
     } else if (warp >= W_LOADER0) {
-        // ================= patch loaders (256 threads) =================
+        // ================= patch loaders (LOADER_THREADS threads) =================
         // The loader's instruction stream is on the critical path of the small-channel layers, so the
         // tile-independent geometry of every 16-B item is tabulated once; per tile an item costs ~15
         // instructions (bounds test, one multiply-add, two cp.async).
