@@ -309,20 +309,42 @@ def main():
     pipe.ctx.probe_set(L.NET_DETECTOR, -1)
 
     # ---------------- end-to-end with host frames (e2e): pinned H2D + hot path + D2H of records
-    # Each lane does its own H2D -> hot path -> D2H on its stream; the lanes overlap each other (copies of one batch
-    # under the kernels of the other), and the host reads step s - n_lanes back while step s runs.
+    # One copy stream keeps the PCIe link busy back to back (2 device frame buffers per lane); lane s % n_lanes runs
+    # step s on its own stream once its frames have landed, then queues the D2H of the records; the host reads step
+    # s - n_lanes back while step s runs.
+    copy_stream = torch.cuda.Stream(device=dev)
+    n_buf = 2 * n_lanes
+    e2e_frames = dev_frames + [torch.empty_like(host, device=dev) for _ in range(n_buf - n_lanes)]
+    e2e_fbs = [FrameBatch.from_device(d) for d in e2e_frames]
+    ready = [torch.cuda.Event() for _ in range(n_buf)]
+    consumed = [torch.cuda.Event() for _ in range(n_buf)]
     n_out = [0]
 
     def e2e_loop(steps):
         d2h = 0
+        ahead = 0                                            # copies issued so far
+
+        def issue_copy(i):
+            b = i % n_buf
+            with torch.cuda.stream(copy_stream):
+                if i >= n_buf:
+                    copy_stream.wait_event(consumed[b])     # the step that read this buffer last is done with it
+                e2e_frames[b].copy_(host, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        while ahead < min(n_buf, steps):
+            issue_copy(ahead); ahead += 1
         for s_ in range(steps):
-            ln = s_ % n_lanes
+            ln, b = s_ % n_lanes, s_ % n_buf
             if s_ >= n_lanes:
                 n_out[0] += pipes[ln].collect(0).shape[0]
             with torch.cuda.stream(lanes[ln]):
-                dev_frames[ln].copy_(host, non_blocking=True)
-                pipes[ln].enqueue_device(fbs[ln], CONF, IOU, MIN_AREA, frame_ids, slot=0)
+                lanes[ln].wait_event(ready[b])
+                pipes[ln].enqueue_device(e2e_fbs[b], CONF, IOU, MIN_AREA, frame_ids, slot=0)
+                consumed[b].record(lanes[ln])
                 pipes[ln].enqueue_fetch(0)               # D2H of the step's records, queued behind the step
+            if ahead < steps:
+                issue_copy(ahead); ahead += 1
             d2h += pipe.records.numel() * 4 + 4 + 4 * B
         for ln in range(min(n_lanes, steps)):
             n_out[0] += pipes[ln].collect(0).shape[0]
