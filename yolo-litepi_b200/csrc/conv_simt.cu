@@ -563,7 +563,7 @@ __global__ void maxpool8_kernel(ConvParams p) {
 // image per block, the map held in shared memory; writes the three pooled slices next to each other in
 // the concat buffer.  Replaces three launches that each re-read the map from L2.
 __global__ void __launch_bounds__(256) sppf3_kernel(ConvParams p, int slice_stride) {
-    extern __shared__ float s_map[];                    // [2][H*W][8]
+    extern __shared__ float s_map[];                    // [3][H*W][8]: ping, pong, row maxima
     const int hw = p.H * p.W;
     float* a = s_map;
     float* b = s_map + hw * 8;
@@ -577,19 +577,26 @@ __global__ void __launch_bounds__(256) sppf3_kernel(ConvParams p, int slice_stri
         for (int k = 0; k < 8; ++k) a[px * 8 + k] = v[k];
     }
     __syncthreads();
+    float* tmp = s_map + 2 * hw * 8;                    // row maxima (the 5x5 window is separable: 5 + 5 taps instead of 25)
     for (int pass = 0; pass < 3; ++pass) {
+        for (int e = threadIdx.x; e < hw * 8; e += blockDim.x) {
+            const int px = e >> 3, k = e & 7;
+            const int oy = px / p.W, ox = px - oy * p.W;
+            float m = -INFINITY;
+            for (int kx = -2; kx <= 2; ++kx) {
+                const int ix = ox + kx;
+                if (ix >= 0 && ix < p.W) m = fmaxf(m, a[(oy * p.W + ix) * 8 + k]);
+            }
+            tmp[e] = m;
+        }
+        __syncthreads();
         for (int e = threadIdx.x; e < hw * 8; e += blockDim.x) {
             const int px = e >> 3, k = e & 7;
             const int oy = px / p.W, ox = px - oy * p.W;
             float m = -INFINITY;
             for (int ky = -2; ky <= 2; ++ky) {
                 const int iy = oy + ky;
-                if (iy < 0 || iy >= p.H) continue;
-                for (int kx = -2; kx <= 2; ++kx) {
-                    const int ix = ox + kx;
-                    if (ix < 0 || ix >= p.W) continue;
-                    m = fmaxf(m, a[(iy * p.W + ix) * 8 + k]);
-                }
+                if (iy >= 0 && iy < p.H) m = fmaxf(m, tmp[(iy * p.W + ox) * 8 + k]);
             }
             b[e] = m;
         }
@@ -778,7 +785,7 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             // SPPF cascade: this 5x5 s1 pool feeds a second and a third one, all slices of one buffer
             if (v8 && op.ksize == 5 && op.stride == 1 && oi + 2 < net.ops.size() &&
                 !(ctx->probe_net == net_id && (ctx->probe_op == -2 || (ctx->probe_op >= (int)oi && ctx->probe_op <= (int)oi + 2))) &&
-                (size_t)p.H * p.W * 64 <= 48 * 1024) {
+                (size_t)p.H * p.W * 96 <= 48 * 1024) {
                 const lp_op_desc& o1 = net.ops[oi + 1];
                 const lp_op_desc& o2 = net.ops[oi + 2];
                 const int step = o1.out_coff - op.out_coff;
@@ -787,7 +794,7 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                            b.in_coff == a.out_coff && b.out_buf == a.out_buf && b.out_seg_len == 0 && b.out_cstride <= 1;
                 };
                 if (chained(op, o1) && chained(o1, o2) && o2.out_coff - o1.out_coff == step && step >= op.cout) {
-                    sppf3_kernel<<<batch * (p.cout / 8), 256, (size_t)p.H * p.W * 64, st>>>(p, step);
+                    sppf3_kernel<<<batch * (p.cout / 8), 256, (size_t)p.H * p.W * 96, st>>>(p, step);
                     oi += 2;                          // the two downstream pools are done
                     break;
                 }
