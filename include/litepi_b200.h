@@ -105,17 +105,20 @@ int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int n_bufs,
 /* 1 = use tcgen05 kernels where an op has wtc_off >= 0 (default), 0 = SIMT only. */
 int lp_set_tensor_core(lp_ctx* ctx, int enable);
 
-/* Fused classifier: the whole ShuffleNetV2 forward of `group` ROIs in one persistent CTA, driven by a
- * host-built step list (plan.py build_fused_classifier; struct FStep in csrc/shufflenet_fused.cu, 18 x int32
- * per step, device memory) over an fp32 weight blob.  When loaded, lp_classify uses it instead of the
- * layer-by-layer plan; lp_set_fused_classifier(ctx, 0) switches back.  smem_bytes = extent of the activation
- * map, back_bytes = extent the back end (steps n_front..) still uses; behind it the shared memory holds
- * astage_bytes of fp16 activation staging and the back end's weight stages.  weights16 (device, may be NULL) =
- * split-f16 weights [cout_p8][hi|lo][L] of the back end's pointwise layers (FStep.w16_off), which then run on
- * the tensor cores (mma.sync, Ahi*Bhi + Alo*Bhi + Ahi*Blo in fp32). */
-int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_back, const float* weights,
-                             const void* weights16, int group, int in_hw, int n_classes, size_t smem_bytes,
-                             size_t back_bytes, size_t astage_bytes, float mean, float stdv);
+/* Fused classifier: the whole ShuffleNetV2 forward inside one persistent CTA per SM, driven by a host-built
+ * program (plan.py build_fused_classifier -> FusedProgram; struct FStep in csrc/shufflenet_fused.cu, 18 x int32
+ * per step, device memory) over an fp32 weight blob.  Three step lists: front (n_front steps, per ROI), middle
+ * (n_mid, per ROI; ends by parking park_floats floats per ROI in global memory), tail (n_tail, the CTA's ROIs
+ * stacked tail_group at a time so that 73 % of the weight stream is read once per group).  When loaded,
+ * lp_classify uses it instead of the layer-by-layer plan; lp_set_fused_classifier(ctx, 0) switches back.
+ * smem_bytes = extent of the front/middle activation map, back_bytes = extent the middle still uses (behind it:
+ * astage_bytes of fp16 activation staging and the middle's weight stages), tail_bytes = extent of the tail's map.
+ * weights16 (device, may be NULL) = split-f16 weights [cout_p8][hi|lo][L] of the middle's pointwise layers
+ * (FStep.w16_off), which then run on the tensor cores (mma.sync, Ahi*Bhi + Alo*Bhi + Ahi*Blo in fp32). */
+int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_mid, int n_tail,
+                             const float* weights, const void* weights16, int tail_group, int in_hw, int n_classes,
+                             size_t smem_bytes, size_t back_bytes, size_t astage_bytes, size_t tail_bytes,
+                             int park_floats, float mean, float stdv);
 int lp_set_fused_classifier(lp_ctx* ctx, int enable);
 
 /* ---- K1: letterbox.  Replaces letterbox() + cvtColor (e2e.py:66-86, :224-225).

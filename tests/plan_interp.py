@@ -85,59 +85,76 @@ def detect_tail_cpu(head: torch.Tensor, in_size: int = 640):
     return out
 
 
-def run_fused_cpu(steps, weights, x_u8, group, n_front, smem_bytes, mean=0.18, std=0.34):
-    """CPU execution of the fused-classifier step list with the SAME shared-memory map (a flat float
-    array), so buffer overlays and offsets are validated, not just the math.  x_u8 [R,64,64,3]."""
-    W = np.asarray(weights, np.float32)
-    R = x_u8.shape[0]
-    G = group
-    logits = None
+def run_fused_cpu(prog, x_u8, grid: int = 2, mean=0.18, std=0.34):
+    """CPU execution of the fused-classifier program (plan.FusedProgram) with the SAME shared-memory maps (flat float
+    arrays, NaN-initialised), so buffer overlays and offsets are validated, not just the math.  Mirrors the kernel's
+    schedule: ``grid`` CTAs, CTA b owns ROIs b, b + grid, ...; per ROI front then middle (parked in "global"
+    memory), then the tail over up to tail_group of the CTA's ROIs stacked as rows.  x_u8 [R,64,64,3]."""
+    steps, W = prog.steps, np.asarray(prog.weights, np.float32)
+    R, GT = x_u8.shape[0], prog.tail_group
     norm = ((np.arange(256, dtype=np.float32) / np.float32(255) - np.float32(mean)) / np.float32(std)).astype(np.float32)
-    out_logits = []
-    for r0 in range(0, R, G):
-        ng = min(G, R - r0)
-        sm = np.full(smem_bytes // 4, np.nan, np.float32)
-        for pas in range(ng + 1):
-            back = pas == ng
-            rng = range(n_front, len(steps)) if back else range(0, n_front)
-            rois = G if back else 1
-            for si in rng:
-                (op, src, dst, src_C, src_off, dst_C, dst_off, dst_cs, cin, cout, H, Wd, stride, relu, w_off, b_off,
-                 roi_stride, _) = [int(v) for v in steps[si]]
-                if not back:
-                    dst += pas * roi_stride
-                if op in (2, 4):
-                    Ho, Wo = H, Wd
-                else:
-                    Ho, Wo = (H + 2 - 3) // stride + 1, (Wd + 2 - 3) // stride + 1
-                if op == 0:        # conv1 from the u8 crop
-                    img = torch.from_numpy(norm[x_u8[r0 + pas]]).permute(2, 0, 1)[None]
-                    cp = (cout + 3) // 4 * 4
-                    w = torch.from_numpy(W[w_off:w_off + 27 * cp].reshape(3, 3, 3, cp)[..., :cout]).permute(3, 2, 0, 1)
-                    y = torch.relu(F.conv2d(img, w, torch.from_numpy(W[b_off:b_off + cout]), stride=2, padding=1))
-                    sm[dst:dst + Ho * Wo * dst_C] = y[0].permute(1, 2, 0).reshape(-1).numpy()
-                    continue
-                src_t = torch.from_numpy(sm[src:src + rois * H * Wd * src_C].reshape(rois, H, Wd, src_C).copy())
-                if op == 1:
-                    y = F.max_pool2d(src_t[..., src_off:src_off + cout].permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
-                elif op == 2:
-                    cp = (cout + 3) // 4 * 4
-                    w = torch.from_numpy(W[w_off:w_off + cin * cp].reshape(cin, cp)[:, :cout])
-                    y = src_t[..., src_off:src_off + cin] @ w + torch.from_numpy(W[b_off:b_off + cout])
-                    if relu:
-                        y = torch.relu(y)
-                elif op == 3:
-                    w = torch.from_numpy(W[w_off:w_off + 9 * cout].reshape(3, 3, cout)).permute(2, 0, 1).unsqueeze(1)
-                    y = F.conv2d(src_t[..., src_off:src_off + cout].permute(0, 3, 1, 2), w, torch.from_numpy(W[b_off:b_off + cout]),
-                                 stride=stride, padding=1, groups=cout).permute(0, 2, 3, 1)
-                elif op == 4:
-                    y = src_t[..., src_off:src_off + cout]
-                elif op == 5:
-                    m = src_t[..., :cin].mean(dim=(1, 2))
-                    w = torch.from_numpy(W[w_off:w_off + cin * cout].reshape(cin, cout))
-                    out_logits.append((m @ w + torch.from_numpy(W[b_off:b_off + cout]))[:ng].numpy())
-                    continue
-                assert not torch.isnan(y[:ng if back else 1]).any(), f"step {si} reads uninitialised shared memory"
-                d = sm[dst:dst + rois * Ho * Wo * dst_C].reshape(rois, Ho, Wo, dst_C)
-                d[..., dst_off:dst_off + dst_cs * cout:dst_cs] = y.numpy()
-    return np.concatenate(out_logits, 0)
+    logits = np.full((R, int(steps[-1][9])), np.nan, np.float32)
+
+    def run_steps(sm, rng, rois, roi_ids, park):
+        for si in rng:
+            (op, src, dst, src_C, src_off, dst_C, dst_off, dst_cs, cin, cout, H, Wd, stride, relu, w_off, b_off,
+             roi_stride, _) = [int(v) for v in steps[si]]
+            if op in (2, 4, 6, 7):
+                Ho, Wo = H, Wd
+            else:
+                Ho, Wo = (H + 2 - 3) // stride + 1, (Wd + 2 - 3) // stride + 1
+            if op == 0:        # conv1 from the u8 crop
+                img = torch.from_numpy(norm[x_u8[roi_ids[0]]]).permute(2, 0, 1)[None]
+                cp = (cout + 3) // 4 * 4
+                w = torch.from_numpy(W[w_off:w_off + 27 * cp].reshape(3, 3, 3, cp)[..., :cout]).permute(3, 2, 0, 1)
+                y = torch.relu(F.conv2d(img, w, torch.from_numpy(W[b_off:b_off + cout]), stride=2, padding=1))
+                sm[dst:dst + Ho * Wo * dst_C] = y[0].permute(1, 2, 0).reshape(-1).numpy()
+                continue
+            if op == 7:        # load the parked tensors of the stacked ROIs
+                for g, rid in enumerate(roi_ids):
+                    sm[dst + g * roi_stride:dst + (g + 1) * roi_stride] = park[rid]
+                continue
+            src_t = torch.from_numpy(sm[src:src + rois * H * Wd * src_C].reshape(rois, H, Wd, src_C).copy())
+            if op == 6:        # park the middle's result
+                assert not torch.isnan(src_t).any()
+                park[roi_ids[0]] = src_t.reshape(-1).numpy().copy()
+                continue
+            if op == 1:
+                y = F.max_pool2d(src_t[..., src_off:src_off + cout].permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+            elif op == 2:
+                cp = (cout + 3) // 4 * 4
+                w = torch.from_numpy(W[w_off:w_off + cin * cp].reshape(cin, cp)[:, :cout])
+                y = src_t[..., src_off:src_off + cin] @ w + torch.from_numpy(W[b_off:b_off + cout])
+                if relu:
+                    y = torch.relu(y)
+            elif op == 3:
+                w = torch.from_numpy(W[w_off:w_off + 9 * cout].reshape(3, 3, cout)).permute(2, 0, 1).unsqueeze(1)
+                y = F.conv2d(src_t[..., src_off:src_off + cout].permute(0, 3, 1, 2), w, torch.from_numpy(W[b_off:b_off + cout]),
+                             stride=stride, padding=1, groups=cout).permute(0, 2, 3, 1)
+            elif op == 4:
+                y = src_t[..., src_off:src_off + cout]
+            elif op == 5:
+                m = src_t[..., :cin].mean(dim=(1, 2))
+                w = torch.from_numpy(W[w_off:w_off + cin * cout].reshape(cin, cout))
+                out = (m @ w + torch.from_numpy(W[b_off:b_off + cout])).numpy()
+                for g, rid in enumerate(roi_ids):
+                    logits[rid] = out[g]
+                continue
+            assert not torch.isnan(y).any(), f"step {si} reads uninitialised shared memory"
+            d = sm[dst:dst + rois * Ho * Wo * dst_C].reshape(rois, Ho, Wo, dst_C)
+            d[..., dst_off:dst_off + dst_cs * cout:dst_cs] = y.numpy()
+
+    nf, nm = prog.n_front, prog.n_mid
+    for b in range(grid):
+        mine = list(range(b, R, grid))
+        for k0 in range(0, len(mine), GT):
+            chunk = mine[k0:k0 + GT]
+            park = {}
+            for rid in chunk:
+                sm = np.full(prog.smem_bytes // 4, np.nan, np.float32)
+                run_steps(sm, range(0, nf), 1, [rid], park)
+                run_steps(sm, range(nf, nf + nm), 1, [rid], park)
+            sm = np.full(prog.tail_bytes // 4, np.nan, np.float32)
+            run_steps(sm, range(nf + nm, len(steps)), len(chunk), chunk, park)
+    assert not np.isnan(logits).any()
+    return logits

@@ -77,6 +77,22 @@ def test_classifier_plan_reproduces_torchvision():
     assert float((logits - ref).abs().max()) < 1e-5
 
 
+def test_fused_classifier_program_reproduces_torchvision():
+    """the step lists the fused kernel executes (front / middle / tail with 3 ROIs stacked), run on the CPU with the
+    same shared-memory maps: offsets, overlays and the park/load hand-off are right if torchvision is reproduced"""
+    from plan_interp import run_fused_cpu
+    model = PR.build_shufflenet(49, seed=5)
+    x = np.random.default_rng(2).integers(0, 256, (7, 64, 64, 3), dtype=np.uint8)
+    xin = (torch.from_numpy(x.astype(np.float32)) / 255 - 0.18) / 0.34
+    with torch.no_grad():
+        ref = model(xin.permute(0, 3, 1, 2)).numpy()
+    for gt in (1, 3):
+        prog = plan.build_fused_classifier(model.state_dict(), tail_group=gt)
+        assert prog.n_front == 7 and prog.n_front + prog.n_mid + prog.n_tail == len(prog.steps)
+        got = run_fused_cpu(prog, x, grid=2)
+        assert float(np.abs(got - ref).max()) < 1e-4
+
+
 def test_plan_rejects_foreign_graph(v1_paths, tmp_path):
     model = ncnn_model.load_ncnn(*v1_paths)
     model.c2f_depths = [1, 2, 2]

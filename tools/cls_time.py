@@ -6,7 +6,7 @@ import numpy as np, torch
 import litepi_b200
 from oracle import pipeline_ref as PR
 ref = PR.build_shufflenet(49, seed=0)
-for G in (1, 2, 3):
+for G in (1, 2, 3, 4):
     clf = litepi_b200.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=ref.state_dict(), max_batch=1024, fused_group=G)
     for n in (148, 296, 333, 444, 1024):
         x = torch.randint(0, 255, (n, 64, 64, 3), dtype=torch.uint8, device=clf.device)

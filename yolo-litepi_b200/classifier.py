@@ -31,7 +31,7 @@ class B200Classifier:
     def __init__(self, model_path: Optional[str], arch: str = "shufflenetv2", num_classes: int = 58,
                  input_size: int = 64, device="cpu", state_dict: Optional[dict] = None,
                  cuda_device: int = 0, max_batch: int = 256, seed: Optional[int] = None,
-                 tensor_cores: bool = True, fused: bool = True, fused_group: int = 1):
+                 tensor_cores: bool = True, fused: bool = True, fused_group: int = 3):
         # `device` is the reference's torch device string (e2e.py:354); this backend always runs on
         # cuda:`cuda_device`.  Only shufflenetv2 is implemented (ValueError like e2e.py:335 otherwise).
         if arch != "shufflenetv2":
@@ -76,16 +76,16 @@ class B200Classifier:
         # layer-by-layer plan above stays loaded as the cross-check (set_fused(False))
         self.fused = self._has_fused = bool(fused) and self.input_size == 64
         if self.fused:
-            steps, fw, n_front, n_back, smem, back, w16, astage = build_fused_classifier(sd, group=fused_group,
-                                                                                          in_size=self.input_size)
+            prog = build_fused_classifier(sd, in_size=self.input_size, tail_group=fused_group)
             with torch.cuda.device(self.device):
-                self.fused_steps = torch.from_numpy(steps).to(self.device)
-                self.fused_weights = torch.from_numpy(fw).to(self.device)
-                self.fused_weights16 = torch.from_numpy(w16.view(np.int16)).to(self.device)
-            L.check(L.lib().lp_fused_classifier_load(self.ctx.handle, _ptr(self.fused_steps), n_front, n_back,
-                                                     _ptr(self.fused_weights), _ptr(self.fused_weights16), fused_group,
-                                                     self.input_size, self.num_classes, smem, back, astage, 0.18, 0.34),
-                    "lp_fused_classifier_load")
+                self.fused_steps = torch.from_numpy(prog.steps).to(self.device)
+                self.fused_weights = torch.from_numpy(prog.weights).to(self.device)
+                self.fused_weights16 = torch.from_numpy(prog.weights16.view(np.int16)).to(self.device)
+            L.check(L.lib().lp_fused_classifier_load(self.ctx.handle, _ptr(self.fused_steps), prog.n_front, prog.n_mid,
+                                                     prog.n_tail, _ptr(self.fused_weights), _ptr(self.fused_weights16),
+                                                     prog.tail_group, self.input_size, self.num_classes, prog.smem_bytes,
+                                                     prog.back_bytes, prog.astage_bytes, prog.tail_bytes, prog.park_floats,
+                                                     0.18, 0.34), "lp_fused_classifier_load")
         self._cap = 0
         self._alloc(self.max_batch)
 

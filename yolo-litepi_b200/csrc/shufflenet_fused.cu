@@ -16,7 +16,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-enum { FS_CONV1 = 0, FS_MAXPOOL = 1, FS_PW = 2, FS_DW = 3, FS_COPY = 4, FS_MEANFC = 5 };
+enum { FS_CONV1 = 0, FS_MAXPOOL = 1, FS_PW = 2, FS_DW = 3, FS_COPY = 4, FS_MEANFC = 5, FS_STORE = 6, FS_LOAD = 7 };
 
 struct FStep {
     int op;
@@ -27,7 +27,7 @@ struct FStep {
     int H, W, stride;          // input spatial size
     int relu;
     int w_off, b_off;          // float offsets into the weight blob
-    int dst_roi_stride;        // front end: added per ROI index to dst (0 otherwise)
+    int dst_roi_stride;        // FS_STORE / FS_LOAD: floats per ROI parked in global memory between middle and tail
     int w16_off;               // > 0: split-f16 weights of this pointwise layer in the fp16 blob, in units of 16 B (+1); 0: none
 };
 
@@ -270,7 +270,8 @@ __device__ __forceinline__ void pw_layer(const float* __restrict__ in, int in_C,
 __global__ void __launch_bounds__(FUSED_BLOCK, 1)
 shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const int* __restrict__ n_dev, const float* __restrict__ W,
                         const uint4* __restrict__ W16, int astage_off,
-                        const FStep* __restrict__ steps, int n_front, int n_back, int G, int in_hw,
+                        const FStep* __restrict__ steps, int n_front, int n_mid, int n_tail, int GT, float* park,
+                        int tail_off, int tail_floats, int in_hw,
                         float mean, float stdv, float* __restrict__ logits, int n_classes, int wbuf_off,
                         int back_off, int back_floats, long long* dbg, int cs) {
     extern __shared__ __align__(16) float sm[];
@@ -285,7 +286,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
     // regions overlap, so the producer starts a pass only after the compute threads finished the previous one.
     float* wbuf = sm + wbuf_off;                            // [2][WBUF_FLOATS]
     float* wbig = sm + back_off;                            // [2][back_floats]
-    for (int i = tid; i < (n_front + n_back) * (int)(sizeof(FStep) / 4); i += FUSED_BLOCK)
+    for (int i = tid; i < (n_front + n_mid + n_tail) * (int)(sizeof(FStep) / 4); i += FUSED_BLOCK)
         reinterpret_cast<int*>(s_steps)[i] = reinterpret_cast<const int*>(steps)[i];
     if (tid == 0) {
         f_mbar_init(&s_full[0], 1); f_mbar_init(&s_full[1], 1);
@@ -300,11 +301,12 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
     f_cluster_sync();                                        // every CTA's barriers exist before any remote arrive / multicast
     const int img_bytes = in_hw * in_hw * 3;
     const int n_rois = n_dev ? min(n_rois_cap, *n_dev) : n_rois_cap;     // count produced on the device by roi_select
-    const int n_groups = (n_rois + G - 1) / G;
-    // every CTA of a cluster runs the same number of iterations (the weight stream is shared); CTAs whose
-    // group index is past the end compute on stale data and write nothing
-    const int n_iters = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
-
+    // Schedule of a CTA: its ROIs are b, b + grid, b + 2 grid, ...; "rounds" that exist for CTA 0 exist for every CTA
+    // (a CTA without a ROI in the last round computes on stale data and writes nothing: the pass structure, and with
+    // it the weight stream, is uniform over the grid / cluster).  Per chunk of GT rounds: front + middle of each ROI
+    // (the middle parks its result in global memory), then ONE tail pass over the stacked ROIs.
+    const int n_rounds = (n_rois + (int)gridDim.x - 1) / (int)gridDim.x;
+    float* my_park = park + (size_t)blockIdx.x * GT * s_steps[n_front + n_mid - 1].dst_roi_stride;
     if (tid >= FUSED_THREADS) {
         // ================= weight producer warp: replays the step list, one bulk copy per K chunk =========
         // Cluster protocol per chunk: every CTA's producer waits until its own consumers released the stage,
@@ -315,13 +317,17 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
             const uint32_t rank = f_cluster_rank();
             const uint16_t mask = (uint16_t)((1u << cs) - 1u);
             uint32_t ctr = 0, passes = 0;
-            for (int iter = 0; iter < n_iters; ++iter) {
-                for (int pass = 0; pass <= G; ++pass, ++passes) {
-                    const bool back = (pass == G);
-                    const int s_begin = back ? n_front : 0, s_end = back ? n_front + n_back : n_front;
+            for (int rnd0 = 0; rnd0 < n_rounds; rnd0 += GT) {
+                const int ng = min(GT, n_rounds - rnd0);
+                for (int pass = 0; pass <= 2 * ng; ++pass, ++passes) {
+                    // passes 2j, 2j+1: front and middle of stacked ROI j; pass 2*ng: tail
+                    const int kind = pass == 2 * ng ? 2 : (pass & 1);
+                    const bool back = kind == 1;
+                    const int s_begin = kind == 0 ? 0 : (kind == 1 ? n_front : n_front + n_mid);
+                    const int s_end = kind == 0 ? n_front : (kind == 1 ? n_front + n_mid : n_front + n_mid + n_tail);
                     if (passes) f_mbar_wait(&s_phase, (passes - 1) & 1);      // previous pass done: its buffers and stages are free
-                    float* wdst = back ? wbig : wbuf;
-                    const int slot_floats = back ? back_floats : WBUF_FLOATS;
+                    float* wdst = kind == 0 ? wbuf : (kind == 1 ? wbig : sm + tail_off);
+                    const int slot_floats = kind == 0 ? WBUF_FLOATS : (kind == 1 ? back_floats : tail_floats);
                     for (int si = s_begin; si < s_end; ++si) {
                         const FStep& st = s_steps[si];
                         if (st.op != FS_PW) continue;
@@ -366,26 +372,29 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
     } else {
     uint32_t chunk_ctr = 0;
 
-    for (int iter = 0; iter < n_iters; ++iter) {
-        const int group = blockIdx.x + iter * gridDim.x;
-        const int roi0 = group * G;
-        const int ng = max(0, min(G, n_rois - roi0));       // real ROIs of this group (0 for a padding group)
-        for (int pass = 0; pass <= G; ++pass) {
-            // pass < G: front end of ROI `pass`; pass == G: back end of the whole group
-            const bool back = (pass == G);
-            const int s_begin = back ? n_front : 0, s_end = back ? n_front + n_back : n_front;
-            if (!back && pass < ng) {
+    for (int rnd0 = 0; rnd0 < n_rounds; rnd0 += GT) {
+        const int ng = min(GT, n_rounds - rnd0);             // ROIs stacked in this chunk's tail
+        for (int pass = 0; pass <= 2 * ng; ++pass) {
+            const int kind = pass == 2 * ng ? 2 : (pass & 1);   // 0 front, 1 middle, 2 tail
+            const bool back = kind == 1;
+            const int jroi = pass >> 1;                           // stacked index of the ROI of a front / middle pass
+            const int roi = (int)blockIdx.x + (rnd0 + jroi) * (int)gridDim.x;
+            const int s_begin = kind == 0 ? 0 : (kind == 1 ? n_front : n_front + n_mid);
+            const int s_end = kind == 0 ? n_front : (kind == 1 ? n_front + n_mid : n_front + n_mid + n_tail);
+            if (kind == 0 && roi < n_rois) {
                 // stage the u8 crop (16-B copies); the CONV1 step's src is its float offset
-                const uint4* g4 = reinterpret_cast<const uint4*>(in + (size_t)(roi0 + pass) * img_bytes);
+                const uint4* g4 = reinterpret_cast<const uint4*>(in + (size_t)roi * img_bytes);
                 uint4* s4 = reinterpret_cast<uint4*>(sm + s_steps[0].src);
                 for (int i = tid; i < img_bytes / 16; i += FUSED_THREADS) s4[i] = __ldg(g4 + i);
                 CSYNC();
             }
+            const float* wst = kind == 0 ? wbuf : (kind == 1 ? wbig : sm + tail_off);
+            const int wst_floats = kind == 0 ? WBUF_FLOATS : (kind == 1 ? back_floats : tail_floats);
             for (int si = s_begin; si < s_end; ++si) {
                 const FStep& st = s_steps[si];
                 const long long t_step = dbg ? clock64() : 0;
-                const int rois = back ? G : 1;
-                float* dst = sm + st.dst + (back ? 0 : pass * st.dst_roi_stride);
+                const int rois = kind == 2 ? ng : 1;
+                float* dst = sm + st.dst;
                 const float* src = sm + st.src;
                 const int Ho = (st.op == FS_PW || st.op == FS_COPY) ? st.H : (st.H + 2 - 3) / st.stride + 1;
                 const int Wo = (st.op == FS_PW || st.op == FS_COPY) ? st.W : (st.W + 2 - 3) / st.stride + 1;
@@ -453,12 +462,15 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     // tiles * KS within the 512 compute threads (plan.py guarantees tiles <= 512)
                     const int ncg = (st.cout + 3) >> 2;
                     const float* bias = W + st.b_off;
-                    const int rt = rows >= 8 ? 8 : (rows >= 4 ? 4 : (rows >= 2 ? 2 : 1));
-                    const int tiles = ((rows + rt - 1) / rt) * ncg;
+                    // the tiling (and with it the K split = the summation order of every output) is derived from the
+                    // CAPACITY of the pass, not from how many ROIs are stacked this time: a ROI's logits do not depend
+                    // on what else is in the batch
+                    const int rows_cap = (kind == 2 ? GT : 1) * st.H * st.W;
+                    const int rt = rows_cap >= 8 ? 8 : (rows_cap >= 4 ? 4 : (rows_cap >= 2 ? 2 : 1));
+                    const int tiles = ((rows_cap + rt - 1) / rt) * ncg;
                     int ksl = 0;
                     while (ksl < 3 && (tiles << (ksl + 1)) <= FUSED_THREADS) ++ksl;
-#define PW_CALL(RT_) pw_layer<RT_>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, bias, st.relu, ksl, back ? wbig : wbuf, \
-                                   back ? back_floats : WBUF_FLOATS, s_full, s_empty, chunk_ctr)
+#define PW_CALL(RT_) pw_layer<RT_>(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, bias, st.relu, ksl, wst, wst_floats, s_full, s_empty, chunk_ctr)
                     if (rt == 8) PW_CALL(8);
                     else if (rt == 4) PW_CALL(4);
                     else if (rt == 2) PW_CALL(2);
@@ -516,6 +528,22 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     }
                     break;
                 }
+                case FS_STORE: {          // park the middle's result of stacked ROI `jroi` (read back by the tail pass)
+                    const int n4 = (st.H * st.W * st.src_C) >> 2;
+                    const float4* s4 = reinterpret_cast<const float4*>(src);
+                    float4* g4 = reinterpret_cast<float4*>(my_park + (size_t)jroi * st.dst_roi_stride);
+                    for (int i = tid; i < n4; i += FUSED_THREADS) __stcg(g4 + i, s4[i]);
+                    break;
+                }
+                case FS_LOAD: {           // stacked rows: ROI g at dst + g * stride
+                    const int n4 = (st.H * st.W * st.dst_C) >> 2;
+                    for (int g = 0; g < rois; ++g) {
+                        const float4* g4 = reinterpret_cast<const float4*>(my_park + (size_t)g * st.dst_roi_stride);
+                        float4* d4 = reinterpret_cast<float4*>(dst + (size_t)g * st.dst_roi_stride);
+                        for (int i = tid; i < n4; i += FUSED_THREADS) d4[i] = __ldcg(g4 + i);   // written by this CTA earlier: never the read-only path
+                    }
+                    break;
+                }
                 case FS_MEANFC: {
                     // x.mean([2,3]) then fc.  dst = scratch: [rois][cin] means, then [8][rois][64] partial sums.
                     // K is split over 8 thread groups (64 lanes = classes each) so the weight reads are
@@ -552,10 +580,11 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                         CSYNC();
                         for (int t = tid; t < ng * 64; t += FUSED_THREADS) {
                             const int jj = t & 63, g = t >> 6;
-                            if (j0 + jj < st.cout) {
+                            const int rid = (int)blockIdx.x + (rnd0 + g) * (int)gridDim.x;
+                            if (j0 + jj < st.cout && rid < n_rois) {
                                 float acc = __ldg(W + st.b_off + j0 + jj);
                                 for (int k = 0; k < 8; ++k) acc += part[(k * rois + g) * 64 + jj];
-                                logits[(size_t)(roi0 + g) * n_classes + j0 + jj] = acc;
+                                logits[(size_t)rid * n_classes + j0 + jj] = acc;
                             }
                         }
                         CSYNC();
@@ -578,7 +607,9 @@ struct lp_fused_cls {
     const float* weights = nullptr;
     const uint4* weights16 = nullptr;   // split-f16 pointwise weights of the back end (may be null: SIMT pointwise layers)
     int astage_off = 0;                 // float offset of the fp16 activation staging of the tensor-core pointwise layers
-    int n_front = 0, n_back = 0, G = 0, in_hw = 0, n_classes = 0;
+    int n_front = 0, n_mid = 0, n_tail = 0, GT = 1, in_hw = 0, n_classes = 0;
+    float* park = nullptr;              // [sm_count][GT][park_floats]: the middle's results waiting for the tail pass
+    int tail_off = 0, tail_floats = 0;  // tail weight stages (floats): start and size of one
     size_t smem_bytes = 0;
     int wbuf_off = 0;
     int back_off = 0, back_floats = 0;   // back-end weight stages (floats): start and size of one
@@ -589,17 +620,22 @@ struct lp_fused_cls {
 };
 static lp_fused_cls g_fused[16];       // one slot per context id (contexts are few and long-lived)
 
-extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_back, const float* weights,
-                                        const void* weights16, int group, int in_hw, int n_classes, size_t smem_bytes,
-                                        size_t back_bytes, size_t astage_bytes, float mean, float stdv) {
+extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_mid, int n_tail,
+                                        const float* weights, const void* weights16, int tail_group, int in_hw, int n_classes,
+                                        size_t smem_bytes, size_t back_bytes, size_t astage_bytes, size_t tail_bytes,
+                                        int park_floats, float mean, float stdv) {
     LP_CHECK(ctx && steps_dev && weights, "lp_fused_classifier_load: null argument");
-    LP_CHECK(n_front + n_back <= FUSED_MAX_STEPS && n_front > 0 && n_back > 0, "lp_fused_classifier_load: bad step counts");
+    LP_CHECK(n_front + n_mid + n_tail <= FUSED_MAX_STEPS && n_front > 0 && n_mid > 0 && n_tail > 0,
+             "lp_fused_classifier_load: bad step counts");
+    LP_CHECK(tail_group >= 1 && tail_group <= 8 && park_floats > 0 && park_floats % 4 == 0, "lp_fused_classifier_load: bad tail group");
     LP_CHECK(smem_bytes <= 227 * 1024, "lp_fused_classifier_load: %zu B shared memory exceeds 227 KB", smem_bytes);
     LP_CHECK(ctx->fused_slot >= 0 && ctx->fused_slot < 16, "lp_fused_classifier_load: too many contexts");
     lp_fused_cls& f = g_fused[ctx->fused_slot];
     f.steps_dev = (const FStep*)steps_dev; f.weights = weights; f.weights16 = (const uint4*)weights16;
-    f.n_front = n_front; f.n_back = n_back;
-    f.G = group; f.in_hw = in_hw; f.n_classes = n_classes; f.mean = mean; f.stdv = stdv;
+    f.n_front = n_front; f.n_mid = n_mid; f.n_tail = n_tail; f.GT = tail_group;
+    f.in_hw = in_hw; f.n_classes = n_classes; f.mean = mean; f.stdv = stdv;
+    if (f.park) { cudaFree(f.park); f.park = nullptr; }
+    LP_CUDA(cudaMalloc(&f.park, (size_t)ctx->sm_count * tail_group * park_floats * sizeof(float)));
     // the host-built map covers the activations; the two weight stages are appended here
     f.wbuf_off = (int)((smem_bytes + 15) / 16 * 4);
     f.smem_bytes = (size_t)f.wbuf_off * 4 + 2 * WBUF_FLOATS * 4;
@@ -618,6 +654,10 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
     f.back_off = f.astage_off + (int)((astage_bytes + 15) / 16 * 4);
     LP_CHECK((size_t)f.back_off * 4 + 2 * WBUF_FLOATS * 4 <= f.smem_bytes, "lp_fused_classifier_load: no room for the back-end weight stages");
     f.back_floats = (int)(((f.smem_bytes / 4 - f.back_off) / 2) & ~(size_t)3);
+    // tail: [stacked activations | stage 0 | stage 1]
+    f.tail_off = (int)((tail_bytes + 15) / 16 * 4);
+    LP_CHECK((size_t)f.tail_off * 4 + 2 * WBUF_FLOATS * 4 <= f.smem_bytes, "lp_fused_classifier_load: tail group %d does not fit", tail_group);
+    f.tail_floats = (int)(((f.smem_bytes / 4 - f.tail_off) / 2) & ~(size_t)3);
     smem_bytes = f.smem_bytes;
     LP_CUDA(cudaFuncSetAttribute(shufflenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     { const char* e = getenv("LP_CLS_CLUSTER"); f.cluster = e ? atoi(e) : 1; if (f.cluster < 1 || f.cluster > 8) f.cluster = 1; }
@@ -629,7 +669,7 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
 int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cudaStream_t st) {
     if (ctx->fused_slot < 0 || ctx->fused_slot >= 16 || !g_fused[ctx->fused_slot].loaded || !ctx->use_fused) return 0;
     const lp_fused_cls& f = g_fused[ctx->fused_slot];
-    const int groups = (n + f.G - 1) / f.G;
+    const int groups = n;
     const int cs = f.cluster;
     int grid = groups < ctx->sm_count ? groups : ctx->sm_count;
     grid = (grid + cs - 1) / cs * cs;
@@ -640,8 +680,8 @@ int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cuda
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, ctx->roi_count_dev, f.weights, f.weights16, f.astage_off, f.steps_dev, f.n_front, f.n_back, f.G,
-                                        f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, f.back_off, f.back_floats, ctx->tc_dbg, cs);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, ctx->roi_count_dev, f.weights, f.weights16, f.astage_off, f.steps_dev, f.n_front, f.n_mid, f.n_tail, f.GT,
+                                        f.park, f.tail_off, f.tail_floats, f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, f.back_off, f.back_floats, ctx->tc_dbg, cs);
     if (le != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(le)); return -2; }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

@@ -490,15 +490,32 @@ def build_classifier_plan(state_dict: dict, in_size: int = 64, mean: float = 0.1
 
 
 # ============================================================================ fused classifier
-FS_CONV1, FS_MAXPOOL, FS_PW, FS_DW, FS_COPY, FS_MEANFC = range(6)
+FS_CONV1, FS_MAXPOOL, FS_PW, FS_DW, FS_COPY, FS_MEANFC, FS_STORE, FS_LOAD = range(8)
 FSTEP_WORDS = 18        # struct FStep in csrc/shufflenet_fused.cu
 
 
-def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
+@dataclass
+class FusedProgram:
+    """What csrc/shufflenet_fused.cu executes: three step lists in one array.  front (per ROI: conv1, max pool,
+    stage2 unit 0), middle (per ROI: stage2 units 1-3, stage3; tensor-core pointwise layers; ends by parking the
+    4x4x232 result in global memory), tail (the CTA's `tail_group` ROIs stacked as rows: stage4, conv5, mean, fc)."""
+    steps: np.ndarray          # int32 [n, 18] (struct FStep)
+    weights: np.ndarray        # fp32 blob
+    weights16: np.ndarray      # split-f16 pointwise weights of the middle
+    n_front: int
+    n_mid: int
+    n_tail: int
+    tail_group: int
+    smem_bytes: int            # extent of the front/middle activation map
+    back_bytes: int            # extent the middle still uses (behind it: fp16 staging + weight stages)
+    astage_bytes: int
+    tail_bytes: int            # extent of the tail's activation map (behind it: weight stages)
+    park_floats: int           # floats per ROI parked in global memory between middle and tail
+
+
+def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, tail_group: int = 3) -> FusedProgram:
     """Step list + fp32 weight blob for the persistent fused ShuffleNetV2 kernel
-    (csrc/shufflenet_fused.cu).  Returns (steps int32 [n, 18], weights f32, n_front, n_back, smem_bytes,
-    back_bytes = extent of the map the back end still uses, weights16 = split-f16 pointwise weights for the
-    tensor-core layers, astage_bytes = their fp16 activation staging).
+    (csrc/shufflenet_fused.cu).  Returns a FusedProgram.
 
     Shared-memory map (floats): Y = G x 7424 (stage tensor A) | scratch.  Back end: B = G x 7424,
     T1 = G x 7424, T2 = G x 3712.  Front end (per ROI) overlays the scratch: u8 crop, conv1 output,
@@ -507,6 +524,8 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
         raise ValueError("the fused classifier is laid out for 64x64 inputs")
     sd = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in state_dict.items()}
     G = int(group)
+    if G != 1:
+        raise ValueError("front end and middle run one ROI at a time; stack ROIs with tail_group")
     blobs: List[np.ndarray] = []
     nf = [0]
 
@@ -599,14 +618,13 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
     step(FS_PW, F_T3, Y, src_C=bf, dst_C=2 * bf, dst_off=1, dst_cs=2, cin=ci, cout=co, H=8, W=8, relu=1, w_off=wo, b_off=bo,
          roi_stride=ymax)
     n_front = len(steps)
-    # ---- back end (G ROIs stacked)
-    X, OUT = Y, B
-    hw = 8
-    for stage, bf in zip((2, 3, 4), widths):
+
+    def emit_units(stage, bf, X, OUT, T1, T2, hw, skip_first):
+        """units of one stage on ping-pong buffers X/OUT with temporaries T1/T2; returns (X, OUT, hw)"""
         u = 0
         while f"stage{stage}.{u}.branch2.0.weight" in sd:
             pre = f"stage{stage}.{u}"
-            if u == 0 and stage == 2:
+            if u == 0 and skip_first:
                 u += 1
                 continue                                              # done in the front end
             if u == 0:                                                # down-sampling unit
@@ -635,20 +653,46 @@ def build_fused_classifier(state_dict: dict, group: int = 2, in_size: int = 64):
                      w_off=wo, b_off=bo)
             X, OUT = OUT, X
             u += 1
+        return X, OUT, hw
+
+    # ---- middle (per ROI): stage2 units 1-3 and stage3 on the tensor cores, result parked in global memory
+    X, OUT, hw = emit_units(2, widths[0], Y, B, T1, T2, 8, True)
+    X, OUT, hw = emit_units(3, widths[1], X, OUT, T1, T2, hw, False)
+    park = hw * hw * 2 * widths[1]                                    # 4 x 4 x 232 floats per ROI
+    step(FS_STORE, X, 0, src_C=2 * widths[1], cout=2 * widths[1], H=hw, W=hw, roi_stride=park)
+    n_mid = len(steps) - n_front
+    # ---- tail (GT ROIs of this CTA stacked as rows): stage4, conv5, mean, fc.  Its weights are 73 % of the stream,
+    # read once for the stacked ROIs.  Own map: IN | T1 | T2 | A | B (conv5's output overlays IN and the head of T1).
+    GT = int(tail_group)
+    bf4 = widths[2]
+    t_in = 0
+    t_t1 = t_in + GT * park
+    t_t2 = t_t1 + GT * hw * hw * bf4                                   # T1 at stage4.0: 4 x 4 x 232 per ROI
+    t_a = t_t2 + GT * (hw // 2) ** 2 * bf4
+    tail_floats = t_a + GT * (hw // 2) ** 2 * 2 * bf4
+    step(FS_LOAD, 0, t_in, dst_C=2 * widths[1], cout=2 * widths[1], H=hw, W=hw, roi_stride=park)
+    # unit 0 reads IN and writes A; the basic units ping-pong between A and the (now dead) IN region
+    X, OUT, hw = emit_units(4, bf4, t_in, t_a, t_t1, t_t2, hw, False)
     wo, bo, ci, co = pw_w("conv5.0", "conv5.1")
-    assert G * hw * hw * c5 <= G * ymax
-    step(FS_PW, X, T1, src_C=2 * widths[2], dst_C=c5, cin=ci, cout=co, H=hw, W=hw, relu=1, w_off=wo, b_off=bo)
-    step(FS_MEANFC, T1, T2, src_C=c5, cin=c5, cout=ncls, H=hw, W=hw, w_off=push(sd["fc.weight"].T.copy()), b_off=push(sd["fc.bias"]))
-    assert G * c5 <= G * t2_roi
-    n_back = len(steps) - n_front
+    c5 = co
+    assert GT * hw * hw * c5 <= t_a - t_t1                            # conv5's output spans T1 and T2 (both dead)
+    step(FS_PW, X, t_t1, src_C=2 * bf4, dst_C=c5, cin=ci, cout=co, H=hw, W=hw, relu=1, w_off=wo, b_off=bo)
+    mscr = t_a if X == t_in else t_in                                  # means + K-split partial sums: the buffer conv5 did not read
+    assert GT * c5 + 8 * GT * 64 <= GT * (hw * hw * 2 * bf4)
+    step(FS_MEANFC, t_t1, mscr, src_C=c5, cin=c5, cout=ncls, H=hw, W=hw, w_off=push(sd["fc.weight"].T.copy()), b_off=push(sd["fc.bias"]))
+    n_tail = len(steps) - n_front - n_mid
     arr = np.asarray(steps, dtype=np.int32)
     assert arr.shape[1] == FSTEP_WORDS
-    back_floats = S + G * (2 * ymax + t2_roi)                        # Y | B | T1 | T2: all the back end touches
-    # fp16 activation staging of the tensor-core pointwise layers: two planes [rows_p16][cin_p16 + 8]
+    back_floats = S + G * (2 * ymax + t2_roi)                        # Y | B | T1 | T2: all the middle touches
+    # fp16 activation staging of the tensor-core pointwise layers (middle only): two planes [rows_p16][cin_p16 + 8]
     astage = 0
-    for st in steps[n_front:]:
+    for st in steps[n_front:n_front + n_mid]:
         if st[0] == FS_PW and st[17] > 0:
             rows_p = (G * st[10] * st[11] + 15) // 16 * 16
             astage = max(astage, 2 * rows_p * ((st[8] + 15) // 16 * 16 + 8) * 2)
+    for st in steps[n_front + n_mid:]:
+        st[17] = 0                                                    # the tail streams fp32 weights
+    arr = np.asarray(steps, dtype=np.int32)
     w16 = np.concatenate(h16) if h16 else np.zeros(8, np.float16)
-    return arr, np.concatenate(blobs), n_front, n_back, total_floats * 4, back_floats * 4, w16, astage
+    return FusedProgram(arr, np.concatenate(blobs), w16, n_front, n_mid, n_tail, GT, total_floats * 4, back_floats * 4,
+                        astage, tail_floats * 4, park)
