@@ -112,13 +112,14 @@ int lp_set_tensor_core(lp_ctx* ctx, int enable);
  * stacked tail_group at a time so that 73 % of the weight stream is read once per group).  When loaded,
  * lp_classify uses it instead of the layer-by-layer plan; lp_set_fused_classifier(ctx, 0) switches back.
  * smem_bytes = extent of the front/middle activation map, back_bytes = extent the middle still uses (behind it:
- * astage_bytes of fp16 activation staging and the middle's weight stages), tail_bytes = extent of the tail's map.
+ * astage_bytes of fp16 activation staging and the middle's weight stages), tail_bytes = extent of the tail's map
+ * (behind it tail_astage_bytes of fp16 staging, when its pointwise layers also have fp16 weights).
  * weights16 (device, may be NULL) = split-f16 weights [cout_p8][hi|lo][L] of the middle's pointwise layers
  * (FStep.w16_off), which then run on the tensor cores (mma.sync, Ahi*Bhi + Alo*Bhi + Ahi*Blo in fp32). */
 int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_mid, int n_tail,
                              const float* weights, const void* weights16, int tail_group, int in_hw, int n_classes,
                              size_t smem_bytes, size_t back_bytes, size_t astage_bytes, size_t tail_bytes,
-                             int park_floats, float mean, float stdv);
+                             size_t tail_astage_bytes, int park_floats, float mean, float stdv);
 int lp_set_fused_classifier(lp_ctx* ctx, int enable);
 
 /* ---- K1: letterbox.  Replaces letterbox() + cvtColor (e2e.py:66-86, :224-225).

@@ -7,7 +7,7 @@ import litepi_b200
 from litepi_b200 import _lib as L, plan
 from oracle import pipeline_ref as PR
 ref = PR.build_shufflenet(49, seed=0)
-clf = litepi_b200.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=ref.state_dict(), max_batch=512)
+clf = litepi_b200.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=ref.state_dict(), max_batch=512, fused_group=int(os.environ.get("LP_FG", "3")))
 n = 148
 x = torch.randint(0, 255, (n, 64, 64, 3), dtype=torch.uint8, device=clf.device)
 clf.classify_device(x); torch.cuda.synchronize()
@@ -16,7 +16,7 @@ L.check(L.lib().lp_debug_tc_timing(clf.ctx.handle, C.c_void_p(dbg.data_ptr())))
 clf.classify_device(x); torch.cuda.synchronize()
 d = dbg.cpu().numpy()
 steps = clf.fused_steps.cpu().numpy()
-names = ["CONV1", "MAXPOOL", "PW", "DW", "COPY", "MEANFC"]
+names = ["CONV1", "MAXPOOL", "PW", "DW", "COPY", "MEANFC", "STORE", "LOAD"]
 tot = d[:len(steps)].sum()
 agg = {}
 for i, st in enumerate(steps):

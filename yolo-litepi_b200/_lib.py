@@ -46,8 +46,8 @@ _PROTOS = {
     "lp_set_tensor_core": (C.c_int, [C.c_void_p, C.c_int]),
     "lp_set_fused_classifier": (C.c_int, [C.c_void_p, C.c_int]),
     "lp_fused_classifier_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                           C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
-                                           C.c_float, C.c_float]),
+                                           C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                           C.c_int, C.c_float, C.c_float]),
     "lp_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "lp_letterbox": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_void_p,

@@ -76,7 +76,8 @@ class B200Classifier:
         # layer-by-layer plan above stays loaded as the cross-check (set_fused(False))
         self.fused = self._has_fused = bool(fused) and self.input_size == 64
         if self.fused:
-            prog = build_fused_classifier(sd, in_size=self.input_size, tail_group=fused_group)
+            prog = build_fused_classifier(sd, in_size=self.input_size, tail_group=fused_group,
+                                          tail_mma=os.environ.get("LP_CLS_TAIL_MMA", "0") == "1")
             with torch.cuda.device(self.device):
                 self.fused_steps = torch.from_numpy(prog.steps).to(self.device)
                 self.fused_weights = torch.from_numpy(prog.weights).to(self.device)
@@ -84,7 +85,8 @@ class B200Classifier:
             L.check(L.lib().lp_fused_classifier_load(self.ctx.handle, _ptr(self.fused_steps), prog.n_front, prog.n_mid,
                                                      prog.n_tail, _ptr(self.fused_weights), _ptr(self.fused_weights16),
                                                      prog.tail_group, self.input_size, self.num_classes, prog.smem_bytes,
-                                                     prog.back_bytes, prog.astage_bytes, prog.tail_bytes, prog.park_floats,
+                                                     prog.back_bytes, prog.astage_bytes, prog.tail_bytes, prog.tail_astage_bytes,
+                                                     prog.park_floats,
                                                      0.18, 0.34), "lp_fused_classifier_load")
         self._cap = 0
         self._alloc(self.max_batch)

@@ -185,6 +185,106 @@ __device__ __forceinline__ void pw_layer_mma(const float* __restrict__ in, int i
     }
 }
 
+// Tensor-core pointwise layer of the TAIL pass: few rows (the CTA's stacked ROIs x 1..16 pixels) and long K, so a weight
+// chunk holds only 2-6 output tiles.  To keep all 16 warps busy the K steps of a tile are split over KSPLIT warps and the
+// partial 16x8 tiles are summed through shared memory in a fixed order (red[tile][slice][128]).  KSPLIT is derived from
+// the capacity of the pass (m_cap row tiles), never from how many ROIs are stacked this time.
+__device__ __forceinline__ void pw_layer_mma_ks(const float* __restrict__ in, int in_C, float* __restrict__ out, int out_C, int dst_cs,
+                                                int rows, int m_cap, int cin, int cout, const float* __restrict__ bias, int relu,
+                                                __half* __restrict__ astage, float* __restrict__ red, const float* __restrict__ wbuf,
+                                                int slot_floats, uint64_t* full, uint64_t* empty, uint32_t& chunk_ctr) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rows_p = (rows + 15) & ~15, cin_p = (cin + 15) & ~15, cout_p = (cout + 7) & ~7;
+    const int LA = cin_p + 8, L = w16_row_halves(cin);
+    __half* Ah = astage;
+    __half* Al = astage + rows_p * LA;
+    for (int e = tid; e < rows_p * (cin_p >> 1); e += FUSED_THREADS) {
+        const int r = e / (cin_p >> 1), c = (e - r * (cin_p >> 1)) * 2;
+        float x0 = 0.f, x1 = 0.f;
+        if (r < rows) {
+            if (c < cin) x0 = in[r * in_C + c];
+            if (c + 1 < cin) x1 = in[r * in_C + c + 1];
+        }
+        const __half2 hi = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(hi);
+        *reinterpret_cast<__half2*>(Ah + r * LA + c) = hi;
+        *reinterpret_cast<__half2*>(Al + r * LA + c) = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    }
+    CSYNC();
+    const int m_tiles = rows_p >> 4, ksteps = cin_p >> 4;
+    const int NN = chunk_couts(cin, cout, slot_floats);
+    constexpr int NW = FUSED_THREADS / 32;
+    for (int n0 = 0; n0 < cout_p; n0 += NN, ++chunk_ctr) {
+        const int nn = min(NN, cout_p - n0);
+        const uint32_t slot = chunk_ctr & 1;
+        f_mbar_wait(&full[slot], (chunk_ctr >> 1) & 1);
+        const __half* Wc = reinterpret_cast<const __half*>(wbuf + slot * slot_floats);      // [nn][2][L]
+        const int n_tiles = nn >> 3;
+        int ksplit = NW / (m_cap * n_tiles);
+        ksplit = ksplit < 1 ? 1 : (ksplit > ksteps ? ksteps : ksplit);
+        if (ksplit > 8) ksplit = 8;
+        const int items = m_tiles * n_tiles * ksplit;
+        for (int item = warp; item < items; item += NW) {
+            const int tile = item / ksplit, slice = item - tile * ksplit;
+            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+            const int ks0 = (slice * ksteps) / ksplit, ks1 = ((slice + 1) * ksteps) / ksplit;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const __half* arow_h = Ah + (mt * 16 + (lane & 15)) * LA + (lane >> 4) * 8;
+            const __half* arow_l = arow_h + rows_p * LA;
+            const __half* brow = Wc + (size_t)(nt * 8 + (lane >> 2)) * 2 * L + (lane & 3) * 2;
+#pragma unroll 2
+            for (int ks = ks0; ks < ks1; ++ks) {
+                uint32_t ah[4], al[4];
+                ldmatrix_x4(ah, arow_h + ks * 16);
+                ldmatrix_x4(al, arow_l + ks * 16);
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(brow + ks * 16);
+                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(brow + ks * 16 + 8);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(brow + L + ks * 16);
+                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(brow + L + ks * 16 + 8);
+                mma_f16(acc, ah, bh0, bh1);
+                mma_f16(acc, al, bh0, bh1);
+                mma_f16(acc, ah, bl0, bl1);
+            }
+            if (ksplit == 1) {                        // whole K in this warp: epilogue straight from the fragments
+                const int c = n0 + nt * 8 + (lane & 3) * 2;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = mt * 16 + (lane >> 2) + 8 * h;
+                    if (r >= rows) continue;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        if (c + j < cout) {
+                            const float v = acc[2 * h + j] + __ldg(bias + c + j);
+                            out[(size_t)r * out_C + (c + j) * dst_cs] = relu ? fmaxf(v, 0.f) : v;
+                        }
+                }
+            } else {
+                *reinterpret_cast<float4*>(red + ((size_t)(tile * ksplit + slice) * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            }
+        }
+        if (ksplit == 1) {
+            f_mbar_arrive(&empty[slot]);
+            continue;
+        }
+        CSYNC();
+        // fixed-order sum of the K slices, then bias / ReLU / shuffle store; element e of a tile belongs to lane e/4
+        for (int t = tid; t < m_tiles * n_tiles * 128; t += FUSED_THREADS) {
+            const int tile = t >> 7, e = t & 127, ln = e >> 2, q = e & 3;
+            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+            float v = 0.f;
+            for (int sl = 0; sl < ksplit; ++sl) v += red[((size_t)(tile * ksplit + sl) * 32 + ln) * 4 + q];
+            const int r = mt * 16 + (ln >> 2) + 8 * (q >> 1);
+            const int c = n0 + nt * 8 + (ln & 3) * 2 + (q & 1);
+            if (r < rows && c < cout) {
+                v += __ldg(bias + c);
+                out[(size_t)r * out_C + c * dst_cs] = relu ? fmaxf(v, 0.f) : v;
+            }
+        }
+        f_mbar_arrive(&empty[slot]);              // 512 arrivals free the stage for the producer
+        CSYNC();                                  // red is reused by the next chunk
+    }
+}
+
 // rows of W that fit one weight stage
 __device__ __forceinline__ int chunk_rows(int cin, int cout, int slot_floats) {
     const int cout_p = (cout + 3) & ~3;
@@ -271,7 +371,7 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 1)
 shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const int* __restrict__ n_dev, const float* __restrict__ W,
                         const uint4* __restrict__ W16, int astage_off,
                         const FStep* __restrict__ steps, int n_front, int n_mid, int n_tail, int GT, float* park,
-                        int tail_off, int tail_floats, int in_hw,
+                        int tail_astage_off, int tail_red_off, int tail_off, int tail_floats, int in_hw,
                         float mean, float stdv, float* __restrict__ logits, int n_classes, int wbuf_off,
                         int back_off, int back_floats, long long* dbg, int cs) {
     extern __shared__ __align__(16) float sm[];
@@ -331,7 +431,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     for (int si = s_begin; si < s_end; ++si) {
                         const FStep& st = s_steps[si];
                         if (st.op != FS_PW) continue;
-                        if (back && st.w16_off > 0) {
+                        if (kind != 0 && st.w16_off > 0) {
                             // tensor-core layer: chunks of output channels, rows of 2 planes x L halves (4*L bytes)
                             const int NN = chunk_couts(st.cin, st.cout, slot_floats), cout_p8 = (st.cout + 7) & ~7;
                             const int row_b = w16_row_halves(st.cin) * 4;
@@ -456,6 +556,12 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     if (back && st.w16_off > 0) {
                         pw_layer_mma(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.b_off, st.relu,
                                      reinterpret_cast<__half*>(sm + astage_off), wbig, back_floats, s_full, s_empty, chunk_ctr);
+                        break;
+                    }
+                    if (kind == 2 && st.w16_off > 0) {
+                        pw_layer_mma_ks(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, (GT * st.H * st.W + 15) >> 4, st.cin, st.cout,
+                                        W + st.b_off, st.relu, reinterpret_cast<__half*>(sm + tail_astage_off), sm + tail_red_off,
+                                        wst, wst_floats, s_full, s_empty, chunk_ctr);
                         break;
                     }
                     // RT = min(8, rows) rows per thread; K split over the largest power of two <= 8 that keeps
@@ -610,6 +716,7 @@ struct lp_fused_cls {
     int n_front = 0, n_mid = 0, n_tail = 0, GT = 1, in_hw = 0, n_classes = 0;
     float* park = nullptr;              // [sm_count][GT][park_floats]: the middle's results waiting for the tail pass
     int tail_off = 0, tail_floats = 0;  // tail weight stages (floats): start and size of one
+    int tail_astage_off = 0, tail_red_off = 0;   // tail: fp16 activation staging and K-slice partial sums of the tensor-core layers
     size_t smem_bytes = 0;
     int wbuf_off = 0;
     int back_off = 0, back_floats = 0;   // back-end weight stages (floats): start and size of one
@@ -623,7 +730,7 @@ static lp_fused_cls g_fused[16];       // one slot per context id (contexts are 
 extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_mid, int n_tail,
                                         const float* weights, const void* weights16, int tail_group, int in_hw, int n_classes,
                                         size_t smem_bytes, size_t back_bytes, size_t astage_bytes, size_t tail_bytes,
-                                        int park_floats, float mean, float stdv) {
+                                        size_t tail_astage_bytes, int park_floats, float mean, float stdv) {
     LP_CHECK(ctx && steps_dev && weights, "lp_fused_classifier_load: null argument");
     LP_CHECK(n_front + n_mid + n_tail <= FUSED_MAX_STEPS && n_front > 0 && n_mid > 0 && n_tail > 0,
              "lp_fused_classifier_load: bad step counts");
@@ -655,7 +762,10 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
     LP_CHECK((size_t)f.back_off * 4 + 2 * WBUF_FLOATS * 4 <= f.smem_bytes, "lp_fused_classifier_load: no room for the back-end weight stages");
     f.back_floats = (int)(((f.smem_bytes / 4 - f.back_off) / 2) & ~(size_t)3);
     // tail: [stacked activations | stage 0 | stage 1]
-    f.tail_off = (int)((tail_bytes + 15) / 16 * 4);
+    // tail: [stacked activations | fp16 staging | K-slice partial sums (16 warps x 128 floats) | stage 0 | stage 1]
+    f.tail_astage_off = (int)((tail_bytes + 15) / 16 * 4);
+    f.tail_red_off = f.tail_astage_off + (int)((tail_astage_bytes + 15) / 16 * 4);
+    f.tail_off = f.tail_red_off + (tail_astage_bytes ? 16 * 128 : 0);
     LP_CHECK((size_t)f.tail_off * 4 + 2 * WBUF_FLOATS * 4 <= f.smem_bytes, "lp_fused_classifier_load: tail group %d does not fit", tail_group);
     f.tail_floats = (int)(((f.smem_bytes / 4 - f.tail_off) / 2) & ~(size_t)3);
     smem_bytes = f.smem_bytes;
@@ -681,7 +791,7 @@ int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cuda
     attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t le = cudaLaunchKernelEx(&cfg, shufflenet_fused_kernel, in, n, ctx->roi_count_dev, f.weights, f.weights16, f.astage_off, f.steps_dev, f.n_front, f.n_mid, f.n_tail, f.GT,
-                                        f.park, f.tail_off, f.tail_floats, f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, f.back_off, f.back_floats, ctx->tc_dbg, cs);
+                                        f.park, f.tail_astage_off, f.tail_red_off, f.tail_off, f.tail_floats, f.in_hw, f.mean, f.stdv, logits, f.n_classes, f.wbuf_off, f.back_off, f.back_floats, ctx->tc_dbg, cs);
     if (le != cudaSuccess) { lp_set_error("shufflenet_fused launch failed: %s", cudaGetErrorString(le)); return -2; }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

@@ -511,9 +511,11 @@ class FusedProgram:
     astage_bytes: int
     tail_bytes: int            # extent of the tail's activation map (behind it: weight stages)
     park_floats: int           # floats per ROI parked in global memory between middle and tail
+    tail_astage_bytes: int = 0 # fp16 activation staging of the tail's tensor-core layers (0: fp32 FMA tail)
 
 
-def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, tail_group: int = 3) -> FusedProgram:
+def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, tail_group: int = 3,
+                           tail_mma: bool = False) -> FusedProgram:
     """Step list + fp32 weight blob for the persistent fused ShuffleNetV2 kernel
     (csrc/shufflenet_fused.cu).  Returns a FusedProgram.
 
@@ -551,7 +553,7 @@ def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, 
         bp = np.zeros(cp, np.float32); bp[:cout] = b
         # tensor-core copy: [cout_p8][hi|lo][L] fp16, L = cin_p16 + pad with L == 4 (mod 32) (csrc w16_row_halves)
         last16[0] = 0
-        if cin <= 128:                  # stage 4 (232) and conv5 (464) are bound by the weight stream: they stay on the fp32 path
+        if True:                        # every pointwise layer gets an fp16 copy; which ones use it is decided per pass
             cin_p = (cin + 15) // 16 * 16
             L = cin_p + ((4 - cin_p) % 32)
             w2 = w.reshape(cout, cin).astype(np.float32)
@@ -690,9 +692,18 @@ def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, 
         if st[0] == FS_PW and st[17] > 0:
             rows_p = (G * st[10] * st[11] + 15) // 16 * 16
             astage = max(astage, 2 * rows_p * ((st[8] + 15) // 16 * 16 + 8) * 2)
+    # tail: rows = the stacked ROIs.  tail_mma: its pointwise layers on the tensor cores with K split over the warps
+    # (csrc pw_layer_mma_ks).  Measured SLOWER than the fp32 path (333 ROIs: 947 vs 797 us at tail_group 2; the fp16
+    # staging and the partial-sum buffer shrink the weight stages, and group 3 no longer fits), hence off by default.
+    tail_astage = 0
     for st in steps[n_front + n_mid:]:
-        st[17] = 0                                                    # the tail streams fp32 weights
+        if st[0] == FS_PW and st[17] > 0:
+            if not tail_mma:
+                st[17] = 0
+                continue
+            rows_p = (GT * st[10] * st[11] + 15) // 16 * 16
+            tail_astage = max(tail_astage, 2 * rows_p * ((st[8] + 15) // 16 * 16 + 8) * 2)
     arr = np.asarray(steps, dtype=np.int32)
     w16 = np.concatenate(h16) if h16 else np.zeros(8, np.float16)
     return FusedProgram(arr, np.concatenate(blobs), w16, n_front, n_mid, n_tail, GT, total_floats * 4, back_floats * 4,
-                        astage, tail_floats * 4, park)
+                        astage, tail_floats * 4, park, tail_astage)
