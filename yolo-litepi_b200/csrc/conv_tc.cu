@@ -22,13 +22,18 @@
 // Epilogue: tcgen05.ld (TMEM lane = pixel) -> bias -> act -> (+residual) -> split -> NHWC stores,
 // written at a channel offset of the destination buffer (concat / C2f views are store patterns).
 //
-// Persistent, warp-specialised CTA (576 threads, one per SM, static round-robin over tiles):
-//   warps 0-7   epilogue (TMEM quadrant = warp % 4, column half = warp / 4)  <- acc_full / -> acc_empty
+// Persistent, warp-specialised CTA (640 threads = 20 warps = 5 per SM sub-partition, which keeps 96 registers per
+// thread; one CTA per SM, static round-robin over tiles):
+//   warps 0-7   epilogue: TMEM -> bias/act/residual/split -> staging tile    <- acc_full, stage_empty / -> acc_empty, stage_full
+//               (TMEM quadrant = warp % 4, column half = warp / 4)
 //   warp  8     weight producer (one lane, bulk TMA)                         <- w_empty   / -> w_full
 //   warp  9     TMEM allocator + MMA issuer (one lane)                       <- patch_full, w_full, acc_empty
-//   warps 10-17 patch loaders (cp.async 16 B, zero-fill halo)                <- patch_empty / -> patch_full
+//   warps 10-15 patch loaders (cp.async 16 B, zero-fill halo)                <- patch_empty / -> patch_full
+//   warps 16-19 store warps: staging tile -> global, coalesced               <- stage_full / -> stage_empty
+//               (two staging buffers; layers with room for only one copy it out with the epilogue warps)
 // Up to 8 patch stages and 4 TMEM accumulator stages keep several tiles in flight: the small-channel
 // layers are HBM/latency-bound, so tiles i+1.. load and tile i-1 drains while tile i is in the tensor core.
+// Consecutive launches are chained with programmatic dependent launch (griddepcontrol).
 #include "common.cuh"
 #include <stdlib.h>
 

@@ -1,18 +1,23 @@
-// K7 fused: the whole ShuffleNetV2 x1.0 forward of a group of ROIs inside ONE persistent CTA.
+// K7 fused: the whole ShuffleNetV2 x1.0 forward inside ONE persistent CTA per SM.
 // Replaces self.model(batch) (src/vntsr/pipeline/e2e.py:393; torchvision shufflenetv2.py) for the 64x64
 // classifier input.  The layer-by-layer plan (71 launches, a few thousand pixels each) is launch- and
 // latency-bound; here every activation of a ROI lives in shared memory (<= 30 KB per ROI after the stem),
-// the folded weights (5.2 MB fp32) stream from L2 into a two-stage shared-memory ring with 1-D bulk TMA
-// (cp.async.bulk + mbarrier) issued by a dedicated producer warp that walks the same step list ahead of
-// the compute warps, and the only other global traffic is the 12 KB u8 crop in and C logits out.
-// fp32 FMA throughout (logit parity ~1e-6).
+// the folded weights stream from L2 into a two-stage shared-memory ring with 1-D bulk TMA (cp.async.bulk +
+// mbarrier) issued by a dedicated producer warp that walks the same step list ahead of the compute warps,
+// and the only other global traffic is the 12 KB u8 crop in, 15 KB parked between middle and tail, and C
+// logits out.
 //
-// The CTA executes a host-built step list (plan.py build_fused_classifier):
-//   front end, per ROI : conv1 3x3 s2 (+ToTensor/Normalize via a 256-entry table) -> maxpool 3x3 s2 ->
-//                        stage2 unit 0 (the only unit whose intermediates exceed 30 KB)
-//   back end, per group: stage2 units 1-3, stage3, stage4, conv5, global mean, fc -- G ROIs stacked as
-//                        GEMM rows so each weight is fetched once per group.
+// The CTA executes a host-built program (plan.py build_fused_classifier -> FusedProgram), three step lists:
+//   front,  per ROI : conv1 3x3 s2 (+ToTensor/Normalize via a 256-entry table) -> maxpool 3x3 s2 ->
+//                     stage2 unit 0 (the only unit whose intermediates exceed 30 KB); fp32 FMA, 2 x 24 KB stages
+//   middle, per ROI : stage2 units 1-3, stage3.  Pointwise layers on the tensor cores (mma.sync m16n8k16,
+//                     split-f16 three-product, fp32 accumulate); weight stages grow over the dead front buffers;
+//                     the 4x4x232 result is parked in global memory
+//   tail,   per CTA : stage4, conv5, global mean, fc for the CTA's ROIs (up to `tail_group`) stacked as GEMM
+//                     rows, so 73 % of the weight bytes are read once per CTA instead of once per ROI
 // channel_shuffle is the store pattern of the producers (dst channel = off + j * 2), chunk is a view.
+// A phase mbarrier keeps the producer from starting a pass before the compute threads finished the previous
+// one (the stage regions of different passes overlap buffers of other passes).
 #include "common.cuh"
 #include <stdlib.h>
 
