@@ -308,6 +308,35 @@ def main():
     probe = pipe.ctx.probe_read()
     pipe.ctx.probe_set(L.NET_DETECTOR, -1)
 
+    # ---------------- per-stage figures (SURVEY.md 8d "roofline per stage"): each stage alone, single lane, CUDA events
+    def timed(fn, n=20):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record(); b.synchronize()
+        return a.elapsed_time(b) / n
+    det_, clf_ = pipe.detector, pipe.classifier
+    t_lb = timed(lambda: det_.letterbox_device(fb0))
+    lb_ = det_.letterbox_device(fb0)
+    t_fw = timed(lambda: det_.forward_device(lb_))
+    out0_ = det_.forward_device(lb_)
+    t_nms = timed(lambda: det_.decode_nms_device(out0_, fb0.h[:B], fb0.w[:B], det_.ratio[:B], det_.pad[:2 * B], CONF, IOU))
+    n_r = pipe.run_device(fb0, CONF, IOU, MIN_AREA, frame_ids)
+    t_rs = timed(lambda: clf_.resize_device(fb0, pipe.roi_xyxy, pipe.roi_src, n_r)) if n_r else 0.0
+    cls_in_ = clf_.resize_device(fb0, pipe.roi_xyxy, pipe.roi_src, n_r) if n_r else None
+    t_cl = timed(lambda: clf_.classify_device(cls_in_)) if n_r else 0.0
+    src_bytes = int(sum(int(h) * int(w) * 3 for h, w in zip(fb0.h[:B], fb0.w[:B])))
+    rx = pipe.roi_xyxy[:n_r].cpu().numpy().astype(np.int64) if n_r else np.zeros((0, 4), np.int64)
+    roi_px = int(((rx[:, 2] - rx[:, 0]) * (rx[:, 3] - rx[:, 1])).sum())
+    stage_rows = [
+        ("K1 letterbox", t_lb, "hbm", (src_bytes + B * 640 * 640 * 3) / 1e9, "GB"),
+        ("K2 detector convs", t_fw, "tensor", 2.0 * sum(macs) * B / 1e12, "TFLOP"),
+        ("K4+K5 decode+NMS", t_nms, "hbm", B * (8400 * 65 * 4) / 1e9, "GB"),
+        ("K6 ROI resize", t_rs, "hbm", (roi_px * 3 + n_r * 64 * 64 * 3) / 1e9, "GB"),
+        ("K7 ShuffleNetV2", t_cl, "tensor", n_r * 23.59e6 / 1e12, "TFLOP"),
+    ]
     # ---------------- end-to-end with host frames (e2e): pinned H2D + hot path + D2H of records
     # One copy stream keeps the PCIe link busy back to back (2 device frame buffers per lane); lane s % n_lanes runs
     # step s on its own stream once its frames have landed, then queues the D2H of the records; the host reads step
@@ -407,6 +436,11 @@ def main():
                      "measured_in": "single-lane pass of the same steps, CUDA events around each launch on its stream",
                      "flops_per_launch": dom_flops},
     }
+    line["stages"] = [{"stage": nm, "ms": round(t, 4), "bound": bd,
+                       "achieved": (work / (t * 1e-3)) if t else None, "unit": "GB/s" if unit == "GB" else "TFLOP/s",
+                       "peak": pk["hbm_gbs"] if bd == "hbm" else peak,
+                       "frac": ((work / (t * 1e-3)) / (pk["hbm_gbs"] if bd == "hbm" else peak)) if t else None}
+                      for nm, t, bd, work, unit in stage_rows]
     if not args.no_cpu_baseline:
         r = cpu_reference_run(48)
         line["cpu_baseline"] = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
