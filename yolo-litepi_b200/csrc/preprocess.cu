@@ -21,71 +21,88 @@ struct FrameTable {
     int top[LP_MAX_TABLE];
 };
 
-// grid (S/4/blockDim.x.., S/ROWS, B); each thread produces 4 consecutive output pixels (12 bytes).
+// grid (S/4/blockDim.x.., S/LB_ROWS, B); each thread produces 4 consecutive output pixels (12 bytes) of LB_ROWS
+// consecutive rows: the column coefficients (two fp64 operations each) are computed once and reused for every row.
+constexpr int LB_ROWS = 8;
 template <int PX>
 __global__ void __launch_bounds__(160) letterbox_kernel(FrameTable tab, int S, uint8_t* __restrict__ out) {
     const int b = blockIdx.z;
-    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
-    if (dy >= S || x0 >= S) return;
+    if (x0 >= S) return;
     const int nw = tab.new_w[b], nh = tab.new_h[b], left = tab.left[b], top = tab.top[b];
     const int W = tab.w[b], H = tab.h[b];
     const uint8_t* __restrict__ src = tab.ptr[b];
     const long long pitch = tab.pitch[b];
-    uint8_t px[PX * 3];
-    const int ry = dy - top;
-    const bool row_in = (ry >= 0 && ry < nh);
     const bool same = (nw == W && nh == H);   // reference skips cv2.resize when the size is unchanged
-    int sy = 0, b0 = 2048, b1 = 0;
-    const uint8_t *r0 = src, *r1 = src;
-    double scale_x = 1.0, scale_y = 1.0;
-    if (row_in) {
-        if (!same) {
-            scale_x = 1.0 / ((double)nw / (double)W);
-            scale_y = 1.0 / ((double)nh / (double)H);
-            lin_coef(ry, scale_y, H, false, sy, b0, b1);
-            int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1);
-            r0 = src + (long long)y0 * pitch;
-            r1 = src + (long long)y1 * pitch;
-        } else {
-            r0 = src + (long long)ry * pitch;
-        }
-    }
+    const double scale_x = same ? 1.0 : 1.0 / ((double)nw / (double)W);
+    const double scale_y = same ? 1.0 : 1.0 / ((double)nh / (double)H);
+    int sxo[PX], sx1o[PX], a0[PX], a1[PX];
+    bool col_in[PX];
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         const int rx = x0 + i - left;
-        uint8_t B = 114, G = 114, R = 114;
-        if (row_in && rx >= 0 && rx < nw) {
-            if (same) {
-                const uint8_t* p = r0 + rx * 3;
-                B = p[0]; G = p[1]; R = p[2];
-            } else {
-                int sx, a0, a1;
-                lin_coef(rx, scale_x, W, true, sx, a0, a1);
-                const int sx1 = min(sx + 1, W - 1);
-                const uint8_t *p00 = r0 + sx * 3, *p01 = r0 + sx1 * 3, *p10 = r1 + sx * 3, *p11 = r1 + sx1 * 3;
-                uint8_t o[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    int t0 = (int)__ldg(p00 + c) * a0 + (int)__ldg(p01 + c) * a1;
-                    int t1 = (int)__ldg(p10 + c) * a0 + (int)__ldg(p11 + c) * a1;
-                    int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
-                    o[c] = (uint8_t)v;
-                }
-                B = o[0]; G = o[1]; R = o[2];
+        col_in[i] = rx >= 0 && rx < nw;
+        sxo[i] = 0; sx1o[i] = 0; a0[i] = 2048; a1[i] = 0;
+        if (col_in[i]) {
+            if (same) { sxo[i] = rx * 3; }
+            else {
+                int sx;
+                lin_coef(rx, scale_x, W, true, sx, a0[i], a1[i]);
+                sxo[i] = sx * 3;
+                sx1o[i] = min(sx + 1, W - 1) * 3;
             }
         }
-        px[i * 3 + 0] = R; px[i * 3 + 1] = G; px[i * 3 + 2] = B;   // BGR -> RGB
     }
-    uint8_t* dst = out + ((size_t)b * S + dy) * (size_t)S * 3 + (size_t)x0 * 3;
-    if (PX == 4 && x0 + 4 <= S) {          // 12 bytes, 4-byte aligned because S*3 and x0*3 are multiples of 4
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        d32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
-        d32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
-        d32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
-    } else {
-        for (int i = 0; i < PX && x0 + i < S; ++i)
-            for (int c = 0; c < 3; ++c) dst[i * 3 + c] = px[i * 3 + c];
+    for (int rr = 0; rr < LB_ROWS; ++rr) {
+        const int dy = blockIdx.y * LB_ROWS + rr;
+        if (dy >= S) return;
+        uint8_t px[PX * 3];
+        const int ry = dy - top;
+        const bool row_in = (ry >= 0 && ry < nh);
+        int sy = 0, b0 = 2048, b1 = 0;
+        const uint8_t *r0 = src, *r1 = src;
+        if (row_in) {
+            if (!same) {
+                lin_coef(ry, scale_y, H, false, sy, b0, b1);
+                const int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1);
+                r0 = src + (long long)y0 * pitch;
+                r1 = src + (long long)y1 * pitch;
+            } else {
+                r0 = src + (long long)ry * pitch;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            uint8_t B = 114, G = 114, R = 114;
+            if (row_in && col_in[i]) {
+                if (same) {
+                    const uint8_t* p = r0 + sxo[i];
+                    B = p[0]; G = p[1]; R = p[2];
+                } else {
+                    const uint8_t *p00 = r0 + sxo[i], *p01 = r0 + sx1o[i], *p10 = r1 + sxo[i], *p11 = r1 + sx1o[i];
+                    uint8_t o[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int t0 = (int)__ldg(p00 + c) * a0[i] + (int)__ldg(p01 + c) * a1[i];
+                        const int t1 = (int)__ldg(p10 + c) * a0[i] + (int)__ldg(p11 + c) * a1[i];
+                        const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+                        o[c] = (uint8_t)v;
+                    }
+                    B = o[0]; G = o[1]; R = o[2];
+                }
+            }
+            px[i * 3 + 0] = R; px[i * 3 + 1] = G; px[i * 3 + 2] = B;   // BGR -> RGB
+        }
+        uint8_t* dst = out + ((size_t)b * S + dy) * (size_t)S * 3 + (size_t)x0 * 3;
+        if (PX == 4 && x0 + 4 <= S) {          // 12 bytes, 4-byte aligned because S*3 and x0*3 are multiples of 4
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+            d32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+            d32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+            d32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+        } else {
+            for (int i = 0; i < PX && x0 + i < S; ++i)
+                for (int c = 0; c < 3; ++c) dst[i * 3 + c] = px[i * 3 + c];
+        }
     }
 }
 
@@ -119,7 +136,7 @@ extern "C" int lp_letterbox(lp_ctx* ctx, const uint8_t* const* frames_h, const i
             if (pad_h) { pad_h[2 * (base + i)] = dw; pad_h[2 * (base + i) + 1] = dh; }
         }
         dim3 block(160, 1, 1);
-        dim3 grid((out_size / 4 + 159) / 160, out_size, n);
+        dim3 grid((out_size / 4 + 159) / 160, (out_size + LB_ROWS - 1) / LB_ROWS, n);
         letterbox_kernel<4><<<grid, block, 0, st>>>(tab, out_size, out + (size_t)base * out_size * out_size * 3);
         LP_LAUNCH_OK(ctx);
     }
