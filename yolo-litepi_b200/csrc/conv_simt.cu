@@ -322,7 +322,7 @@ constexpr int SMALL_SLOTS = 6, SMALL_W_FLOATS = 2048, SMALL_SLOT_FLOATS = SMALL_
 __constant__ float c_small[SMALL_SLOTS][SMALL_SLOT_FLOATS];      // [tap][cin][cout] then bias[cout] at SMALL_W_FLOATS
 
 template <int KS, int STRIDE, int CIN, int COUT, bool U8IN>
-__global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, int slot) {
+__global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, int slot, int post_slot, int post_act) {
     constexpr int PH = (KS == 1) ? 1 : (TILE_H - 1) * STRIDE + KS;
     constexpr int PW = (KS == 1) ? CONV_THREADS : (TILE_W - 1) * STRIDE + KS;
     constexpr int CINP = U8IN ? CIN : ((CIN + 7) / 8) * 8;
@@ -403,6 +403,28 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, 
     }
     const long long opix = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff;
     const long long rpix = (long long)img * p.res.img + ((long long)oy * p.Wo + ox) * p.res.C + p.res.coff;
+    if (post_slot >= 0) {
+        // fused COUT -> COUT 1x1 conv on this pixel's activated outputs (the C2f cv1 that follows the down-sampling
+        // conv): the intermediate tensor is never written.  Weights [cin][cout] + bias in constant slot post_slot.
+        const float* pw = c_small[post_slot];
+        float y[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) y[co] = pw[SMALL_W_FLOATS + co];
+#pragma unroll
+        for (int ci = 0; ci < COUT; ++ci) {
+            const float a = act_apply(acc[ci], p.act);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) y[co] = fmaf(a, pw[ci * COUT + co], y[co]);
+        }
+#pragma unroll
+        for (int g = 0; g < COUT / 8; ++g) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = act_apply(y[g * 8 + i], post_act);
+            st8(p.out, opix + g * 8, v);
+        }
+        return;
+    }
 #pragma unroll
     for (int g = 0; g < COUT / 8; ++g) {
         float v[8];
@@ -746,13 +768,37 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             p.out_cstride == 1 && p.out.fmt == LP_FMT_SPLIT16 &&
             (op.kind == LP_OP_STEM_U8 || p.in.fmt == LP_FMT_SPLIT16) && p.in.coff % 8 == 0 && p.out.coff % 8 == 0) {
             const int slot = net.small_slot[oi];
+            // A 1x1 conv of the same width that is the ONLY consumer of this conv's output (the C2f cv1 behind a
+            // down-sampling conv) is applied in registers: its input tensor is never written or read.
+            int post_slot = -1, post_act = 0;
+            if (op.kind == LP_OP_CONV && op.ksize == 3 && op.res_buf < 0 && oi + 1 < net.ops.size() && net.small_slot[oi + 1] >= 0 &&
+                !(ctx->probe_net == net_id && (ctx->probe_op == -2 || ctx->probe_op == (int)oi || ctx->probe_op == (int)oi + 1))) {
+                const lp_op_desc& o2 = net.ops[oi + 1];
+                bool ok2 = o2.kind == LP_OP_CONV && o2.ksize == 1 && o2.stride == 1 && o2.cin == op.cout && o2.cout == op.cout &&
+                           o2.in_buf == op.out_buf && o2.in_coff == op.out_coff && o2.res_buf < 0 && o2.out_seg_len == 0 &&
+                           o2.out_cstride <= 1 && o2.out_coff % 8 == 0 && net.bufs[o2.out_buf].fmt == LP_FMT_SPLIT16 &&
+                           net.bufs[o2.out_buf].h == ob.h && net.bufs[o2.out_buf].w == ob.w;
+                for (size_t k = 0; ok2 && k < net.ops.size(); ++k)
+                    if (k != oi && k != oi + 1 && (net.ops[k].in_buf == op.out_buf || net.ops[k].res_buf == op.out_buf || net.ops[k].out_buf == op.out_buf))
+                        ok2 = false;
+                if (ok2) {
+                    post_slot = net.small_slot[oi + 1];
+                    post_act = o2.act;
+                    p.out = make_ref(net, o2.out_buf, o2.out_coff, ws, o2.row_off);
+                }
+            }
             const bool ran = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [&](auto kern) {
                 dim3 grid;
                 if (op.ksize == 1) grid = dim3((unsigned)(((long long)batch * p.Ho * p.Wo + CONV_THREADS - 1) / CONV_THREADS), 1, 1);
                 else grid = dim3(((p.Wo + TILE_W - 1) / TILE_W) * ((p.Ho + TILE_H - 1) / TILE_H), 1, batch);
-                kern<<<grid, CONV_THREADS, 0, st>>>(p, slot);
+                kern<<<grid, CONV_THREADS, 0, st>>>(p, slot, post_slot, post_act);
             });
-            if (ran) { LP_LAUNCH_OK(ctx); continue; }
+            if (ran) {
+                LP_LAUNCH_OK(ctx);
+                if (post_slot >= 0) ++oi;            // the 1x1 conv is done
+                continue;
+            }
+            LP_CHECK(post_slot < 0, "small conv dispatch failed after a fusion decision");
         }
         switch (op.kind) {
         case LP_OP_STEM_U8: {
