@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #define ROI_PRECISION_BITS 22
+constexpr int ROI_SPLIT = 4;       // blocks per ROI (bands of output rows)
 
 struct RoiFrames {
     const uint8_t* ptr[LP_MAX_TABLE];
@@ -68,7 +69,9 @@ __global__ void __launch_bounds__(256) roi_resize_kernel(RoiFrames fr, int img_b
     int* by = bx + S * 2;                              // [S][2]
     int* s_misc = by + S * 2;                          // [4]
     uint8_t* tmp = reinterpret_cast<uint8_t*>(s_misc + 4);   // [tmp_rows][S*3]
-    const int r = blockIdx.x;
+    // ROI_SPLIT blocks per ROI, each a band of output rows: a block's critical path (dependent byte loads) was the
+    // kernel's duration, and 333 ROIs leave most of the 148 SMs' warp slots empty anyway
+    const int r = blockIdx.x / ROI_SPLIT, band = blockIdx.x - r * ROI_SPLIT;
     if (r >= n_rois || (n_dev && r >= *n_dev)) return;
     const int img = roi_src[2 * r] - img_base;
     if (img < 0 || img >= LP_MAX_TABLE) return;        // ROI of another 64-image launch chunk
@@ -88,13 +91,15 @@ __global__ void __launch_bounds__(256) roi_resize_kernel(RoiFrames fr, int img_b
     __syncthreads();
     uint8_t* dst = out + (long long)r * S * S * 3;
     const int row_elems = S * 3;
-    int y0 = 0;
-    while (y0 < S) {
+    const int band_rows = (S + ROI_SPLIT - 1) / ROI_SPLIT;
+    int y0 = band * band_rows;
+    const int y_end = min(S, y0 + band_rows);
+    while (y0 < y_end) {
         // group of output rows [y0, y0+G) whose input rows fit in the tmp ring
         if (tid == 0) {
             const int rmin = by[2 * y0];
             int g = 1;
-            while (y0 + g < S && by[2 * (y0 + g)] + by[2 * (y0 + g) + 1] - rmin <= tmp_rows) ++g;
+            while (y0 + g < y_end && by[2 * (y0 + g)] + by[2 * (y0 + g) + 1] - rmin <= tmp_rows) ++g;
             s_misc[0] = g;
             s_misc[1] = rmin;
             s_misc[2] = by[2 * (y0 + g - 1)] + by[2 * (y0 + g - 1) + 1] - rmin;   // rows to resample
@@ -211,7 +216,7 @@ extern "C" int lp_roi_resize(lp_ctx* ctx, const uint8_t* const* frames_h, const 
         RoiFrames fr;
         for (int i = 0; i < n; ++i) { fr.ptr[i] = frames_h[base + i]; fr.pitch[i] = pitch_h[base + i]; }
         for (int i = n; i < LP_MAX_TABLE; ++i) { fr.ptr[i] = nullptr; fr.pitch[i] = 0; }
-        roi_resize_kernel<<<n_rois, 256, smem, st>>>(fr, base, roi_xyxy, roi_src, n_rois, ctx->roi_count_dev, out_size, kmax, tmp_rows, out);
+        roi_resize_kernel<<<n_rois * ROI_SPLIT, 256, smem, st>>>(fr, base, roi_xyxy, roi_src, n_rois, ctx->roi_count_dev, out_size, kmax, tmp_rows, out);
         LP_LAUNCH_OK(ctx);
     }
     return 0;
