@@ -49,7 +49,8 @@ struct lp_net_plan {
     int max_batch = 0;
     size_t workspace_bytes = 0;     // max over bufs of offset + max_batch * image_bytes
     bool loaded = false;
-    std::vector<int> small_slot;    // per op: constant-memory slot of the small-channel conv path, or -1
+    std::vector<int> small_slot;    // per op: >= 0 if the small-channel conv path (weights as kernel parameters) covers it
+    std::vector<std::vector<float>> small_host;   // per op: host copy [weights | bias] for those ops
 };
 
 struct lp_ctx {

@@ -318,11 +318,16 @@ __global__ void __launch_bounds__(CONV_THREADS) stem_u8_kernel(ConvParams p) {
 // weights live in CONSTANT memory: an FFMA takes its weight operand straight from the constant bank, the
 // only shared-memory traffic is one input read per Cout FMAs.  One thread = one output pixel x all Cout.
 // ---------------------------------------------------------------------------------------------
-constexpr int SMALL_SLOTS = 6, SMALL_W_FLOATS = 2048, SMALL_SLOT_FLOATS = SMALL_W_FLOATS + 32;
-__constant__ float c_small[SMALL_SLOTS][SMALL_SLOT_FLOATS];      // [tap][cin][cout] then bias[cout] at SMALL_W_FLOATS
+// Weights travel BY VALUE as a kernel parameter: every FFMA then names its weight as a constant-bank operand with a
+// static offset.  (A __constant__ array indexed by a runtime slot cost one LDC per weight -- ncu: 1350 instructions per
+// pixel for 576 FMAs.)  Kernel parameters may be up to 32 KB since CUDA 12.1; the largest set here is 5.8 KB.
+constexpr int SMALL_W_FLOATS = 2048;
+template <int N> struct SmallW { float v[N]; };      // [tap][cin][cout] then bias[cout]
 
 template <int KS, int STRIDE, int CIN, int COUT, bool U8IN>
-__global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, int slot, int post_slot, int post_act) {
+__global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(const ConvParams p, const SmallW<KS * KS * CIN * COUT + COUT> wt,
+                                                                  const SmallW<COUT * COUT + COUT> pw, int post_on, int post_act) {
+    constexpr int NWT = KS * KS * CIN * COUT;
     constexpr int PH = (KS == 1) ? 1 : (TILE_H - 1) * STRIDE + KS;
     constexpr int PW = (KS == 1) ? CONV_THREADS : (TILE_W - 1) * STRIDE + KS;
     constexpr int CINP = U8IN ? CIN : ((CIN + 7) / 8) * 8;
@@ -388,33 +393,31 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, 
     }
     __syncthreads();
     if (!valid) return;
-    const float* cw = c_small[slot];
     float acc[COUT];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = cw[SMALL_W_FLOATS + co];
+    for (int co = 0; co < COUT; ++co) acc[co] = wt.v[NWT + co];
 #pragma unroll
     for (int t = 0; t < KS * KS; ++t) {
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
             const float a = (KS == 1) ? s_patch[ci][0][tid] : s_patch[ci][ty * STRIDE + t / KS][tx * STRIDE + t % KS];
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(a, cw[(t * CIN + ci) * COUT + co], acc[co]);
+            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(a, wt.v[(t * CIN + ci) * COUT + co], acc[co]);
         }
     }
     const long long opix = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff;
     const long long rpix = (long long)img * p.res.img + ((long long)oy * p.Wo + ox) * p.res.C + p.res.coff;
-    if (post_slot >= 0) {
+    if (post_on) {
         // fused COUT -> COUT 1x1 conv on this pixel's activated outputs (the C2f cv1 that follows the down-sampling
-        // conv): the intermediate tensor is never written.  Weights [cin][cout] + bias in constant slot post_slot.
-        const float* pw = c_small[post_slot];
+        // conv): the intermediate tensor is never written.  Weights [cin][cout] + bias in the second parameter block.
         float y[COUT];
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) y[co] = pw[SMALL_W_FLOATS + co];
+        for (int co = 0; co < COUT; ++co) y[co] = pw.v[COUT * COUT + co];
 #pragma unroll
         for (int ci = 0; ci < COUT; ++ci) {
             const float a = act_apply(acc[ci], p.act);
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) y[co] = fmaf(a, pw[ci * COUT + co], y[co]);
+            for (int co = 0; co < COUT; ++co) y[co] = fmaf(a, pw.v[ci * COUT + co], y[co]);
         }
 #pragma unroll
         for (int g = 0; g < COUT / 8; ++g) {
@@ -440,9 +443,10 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(ConvParams p, 
     }
 }
 
-// returns true if a specialisation exists for this shape (v1 widths 8/16, v2 widths 16/24 stem)
+// Calls f.template run<K,S,CI,CO,U8>() for the specialisation of this shape; false if there is none
+// (v1 widths 8/16, v2 widths 16/24 stem).
 template <typename F> static bool small_dispatch(int ks, int stride, int cin, int cout, bool u8, F&& f) {
-#define LP_SMALL(K, S, CI, CO, U) if (ks == K && stride == S && cin == CI && cout == CO && u8 == U) { f(conv_small_kernel<K, S, CI, CO, U>); return true; }
+#define LP_SMALL(K, S, CI, CO, U) if (ks == K && stride == S && cin == CI && cout == CO && u8 == U) { f.template run<K, S, CI, CO, U>(); return true; }
     LP_SMALL(3, 2, 3, 8, true)
     LP_SMALL(3, 2, 3, 16, true)
     LP_SMALL(3, 2, 8, 16, false)
@@ -452,6 +456,20 @@ template <typename F> static bool small_dispatch(int ks, int stride, int cin, in
 #undef LP_SMALL
     return false;
 }
+struct SmallProbe { template <int K, int S, int CI, int CO, bool U> void run() {} };
+struct SmallLaunch {
+    const ConvParams* p; const float* w_host; const float* post_host; int post_act; int batch; cudaStream_t st;
+    template <int K, int S, int CI, int CO, bool U> void run() {
+        SmallW<K * K * CI * CO + CO> w;
+        memcpy(w.v, w_host, sizeof(w.v));
+        SmallW<CO * CO + CO> pw;
+        if (post_host) memcpy(pw.v, post_host, sizeof(pw.v)); else memset(pw.v, 0, sizeof(pw.v));
+        dim3 grid;
+        if (K == 1) grid = dim3((unsigned)(((long long)batch * p->Ho * p->Wo + CONV_THREADS - 1) / CONV_THREADS), 1, 1);
+        else grid = dim3(((p->Wo + TILE_W - 1) / TILE_W) * ((p->Ho + TILE_H - 1) / TILE_H), 1, batch);
+        conv_small_kernel<K, S, CI, CO, U><<<grid, CONV_THREADS, 0, st>>>(*p, w, pw, post_host ? 1 : 0, post_act);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Memory-bound glue: depthwise 3x3, max pool, nearest x2 upsample, channel-slice copy, mean+FC.
@@ -651,40 +669,23 @@ __global__ void mean_fc_kernel(ConvParams p, float* __restrict__ logits) {
 // ---------------------------------------------------------------------------------------------
 // Plan executor
 // ---------------------------------------------------------------------------------------------
-// Assign constant-memory slots to the small-channel convs of a plan and upload their weights (device ->
-// constant).  Slots are a process-wide resource (one module); plans that come late fall back to the
-// generic kernel.
+// Mark the small-channel convs of a plan that the parameter-weight kernels cover and keep host copies of their
+// weights ([weights | bias]), which travel as kernel parameters at every launch.
 int lp_assign_small_slots(lp_net_plan& net, cudaStream_t st) {
-    static int next_slot = 0;
-    static uint64_t slot_key[SMALL_SLOTS];             // content hash of what each slot holds: equal layers share a slot
     net.small_slot.assign(net.ops.size(), -1);
-    std::vector<float> host(SMALL_SLOT_FLOATS);
+    net.small_host.assign(net.ops.size(), std::vector<float>());
     for (size_t i = 0; i < net.ops.size(); ++i) {
         const lp_op_desc& op = net.ops[i];
         if (op.kind != LP_OP_STEM_U8 && op.kind != LP_OP_CONV) continue;
         const int nw = op.ksize * op.ksize * op.cin * op.cout;
         if (nw > SMALL_W_FLOATS || op.cout > 32) continue;
         if (op.out_seg_len > 0 || op.out_cstride > 1) continue;      // shapes the small kernels do not cover
-        bool have = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [](auto) {});
-        if (!have) continue;
-        LP_CUDA(cudaMemcpyAsync(host.data(), net.weights + op.w_off, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
-        LP_CUDA(cudaMemcpyAsync(host.data() + nw, net.weights + op.b_off, (size_t)op.cout * 4, cudaMemcpyDeviceToHost, st));
-        LP_CUDA(cudaStreamSynchronize(st));
-        uint64_t key = 1469598103934665603ull ^ ((uint64_t)op.ksize << 48 | (uint64_t)op.stride << 40 | (uint64_t)op.cin << 20 | (uint64_t)op.cout);
-        const uint8_t* hb = reinterpret_cast<const uint8_t*>(host.data());
-        for (size_t b = 0; b < (size_t)(nw + op.cout) * 4; ++b) { key ^= hb[b]; key *= 1099511628211ull; }
-        int slot = -1;
-        for (int s2 = 0; s2 < next_slot; ++s2) if (slot_key[s2] == key) { slot = s2; break; }
-        if (slot < 0) {
-            if (next_slot >= SMALL_SLOTS) continue;                  // out of constant memory: generic kernel
-            slot = next_slot++;
-            slot_key[slot] = key;
-            LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.w_off, (size_t)nw * 4, (size_t)slot * SMALL_SLOT_FLOATS * 4,
-                                            cudaMemcpyDeviceToDevice, st));
-            LP_CUDA(cudaMemcpyToSymbolAsync(c_small, net.weights + op.b_off, (size_t)op.cout * 4,
-                                            ((size_t)slot * SMALL_SLOT_FLOATS + SMALL_W_FLOATS) * 4, cudaMemcpyDeviceToDevice, st));
-        }
-        net.small_slot[i] = slot;
+        if (!small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, SmallProbe{})) continue;
+        std::vector<float>& h = net.small_host[i];
+        h.resize((size_t)nw + op.cout);
+        LP_CUDA(cudaMemcpyAsync(h.data(), net.weights + op.w_off, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+        LP_CUDA(cudaMemcpyAsync(h.data() + nw, net.weights + op.b_off, (size_t)op.cout * 4, cudaMemcpyDeviceToHost, st));
+        net.small_slot[i] = (int)i;
     }
     LP_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -767,7 +768,6 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             (p.res.base == nullptr || (p.res.fmt == LP_FMT_SPLIT16 && p.res.coff % 8 == 0)) && p.seg_len == 0 &&
             p.out_cstride == 1 && p.out.fmt == LP_FMT_SPLIT16 &&
             (op.kind == LP_OP_STEM_U8 || p.in.fmt == LP_FMT_SPLIT16) && p.in.coff % 8 == 0 && p.out.coff % 8 == 0) {
-            const int slot = net.small_slot[oi];
             // A 1x1 conv of the same width that is the ONLY consumer of this conv's output (the C2f cv1 behind a
             // down-sampling conv) is applied in registers: its input tensor is never written or read.
             int post_slot = -1, post_act = 0;
@@ -782,17 +782,13 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                     if (k != oi && k != oi + 1 && (net.ops[k].in_buf == op.out_buf || net.ops[k].res_buf == op.out_buf || net.ops[k].out_buf == op.out_buf))
                         ok2 = false;
                 if (ok2) {
-                    post_slot = net.small_slot[oi + 1];
+                    post_slot = (int)oi + 1;
                     post_act = o2.act;
                     p.out = make_ref(net, o2.out_buf, o2.out_coff, ws, o2.row_off);
                 }
             }
-            const bool ran = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, [&](auto kern) {
-                dim3 grid;
-                if (op.ksize == 1) grid = dim3((unsigned)(((long long)batch * p.Ho * p.Wo + CONV_THREADS - 1) / CONV_THREADS), 1, 1);
-                else grid = dim3(((p.Wo + TILE_W - 1) / TILE_W) * ((p.Ho + TILE_H - 1) / TILE_H), 1, batch);
-                kern<<<grid, CONV_THREADS, 0, st>>>(p, slot, post_slot, post_act);
-            });
+            SmallLaunch sl{&p, net.small_host[oi].data(), post_slot >= 0 ? net.small_host[post_slot].data() : nullptr, post_act, batch, st};
+            const bool ran = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, sl);
             if (ran) {
                 LP_LAUNCH_OK(ctx);
                 if (post_slot >= 0) ++oi;            // the 1x1 conv is done
