@@ -332,7 +332,16 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(const ConvPara
     constexpr int PW = (KS == 1) ? CONV_THREADS : (TILE_W - 1) * STRIDE + KS;
     constexpr int CINP = U8IN ? CIN : ((CIN + 7) / 8) * 8;
     __shared__ float s_patch[CINP][PH][PW + 1];
+    __shared__ float s_lut[U8IN ? 256 : 1];             // u8 -> normalised float, the reference's own operations (bit-identical)
     const int tid = threadIdx.x;
+    if (U8IN) {
+        for (int i = tid; i < 256; i += CONV_THREADS) {
+            float x = __fdiv_rn((float)i, 255.f);
+            if (p.in_scale_std != 1.f || p.in_scale_mean != 0.f) x = __fdiv_rn(__fsub_rn(x, p.in_scale_mean), p.in_scale_std);
+            s_lut[i] = x;
+        }
+        __syncthreads();
+    }
     int img, oy, ox, ty = 0, tx = tid, tile_y0 = 0, tile_x0 = 0;
     bool valid;
     if (KS == 1) {
@@ -370,11 +379,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_small_kernel(const ConvPara
                 if (in) {
                     const uint8_t* q = (const uint8_t*)p.in.base + (long long)img * p.in.img + ((long long)iy * p.W + ix) * 3;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float x = __fdiv_rn((float)q[c], 255.f);
-                        if (p.in_scale_std != 1.f || p.in_scale_mean != 0.f) x = __fdiv_rn(__fsub_rn(x, p.in_scale_mean), p.in_scale_std);
-                        v[c] = x;
-                    }
+                    for (int c = 0; c < 3; ++c) v[c] = s_lut[q[c]];
                 }
                 s_patch[0][py][px] = v[0]; s_patch[1][py][px] = v[1]; s_patch[2][py][px] = v[2];
             } else {
