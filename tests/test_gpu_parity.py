@@ -509,3 +509,25 @@ def test_optimized_roi_mode(lp, v1_paths, clf):
     assert np.array_equal(pipe.classifier.cls_in[:n].cpu().numpy(), np.stack(want_in))
     with pytest.raises(ValueError):
         lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, roi_mode="fast")
+
+
+def test_async_step_api_equals_synchronous(lp, v1_paths, clf):
+    """enqueue_device / enqueue_fetch / collect (no host round trip inside a step, device-side ROI count, double-buffered
+    host mirrors) return exactly the records of run_device + fetch_records, also when two steps are in flight."""
+    from litepi_b200 import synth
+    _, ref = clf
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, max_batch=8,
+                           classifier_state_dict=ref.state_dict(), seed=0)
+    fa = lp.detector.FrameBatch.from_host([synth.vn_frame(i) for i in range(8)], pipe.device)
+    fb = lp.detector.FrameBatch.from_host([synth.vn_frame(i) for i in range(8, 14)] + [np.full((681, 1198, 3), 127, np.uint8)], pipe.device)
+    want_a = pipe.fetch_records(pipe.run_device(fa, 0.25, 0.45, 50))
+    want_b = pipe.fetch_records(pipe.run_device(fb, 0.25, 0.45, 50))
+    assert want_a.shape[0] > 0 and want_b.shape[0] > 0
+    pipe.enqueue_device(fa, 0.25, 0.45, 50, slot=0); pipe.enqueue_fetch(0)
+    pipe.enqueue_device(fb, 0.25, 0.45, 50, slot=1); pipe.enqueue_fetch(1)
+    got_a, got_b = pipe.collect(0), pipe.collect(1)
+    assert np.array_equal(got_a, want_a) and np.array_equal(got_b, want_b)
+    # a batch with nothing in it
+    blank = lp.detector.FrameBatch.from_host([np.full((480, 640, 3), 90, np.uint8)] * 2, pipe.device)
+    pipe.enqueue_device(blank, 0.25, 0.45, 50, slot=0); pipe.enqueue_fetch(0)
+    assert pipe.collect(0).shape == (0, 9)
