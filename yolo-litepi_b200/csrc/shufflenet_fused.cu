@@ -619,6 +619,32 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     break;
                 }
                 case FS_MAXPOOL: {
+                    if (Wo == 16 && st.W == 32) {
+                        // task = (channel, output row): the three input rows are scanned once (33 loads for 16 outputs)
+                        for (int task = tid; task < Ho * st.cout; task += FUSED_THREADS) {
+                            const int c = task % st.cout, oy = task / st.cout;
+                            float m[16];
+#pragma unroll
+                            for (int ox = 0; ox < 16; ++ox) m[ox] = -INFINITY;
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky) {
+                                const int iy = oy * 2 - 1 + ky;
+                                if (iy < 0 || iy >= st.H) continue;
+                                const float* rp = src + (size_t)iy * 32 * st.src_C + st.src_off + c;
+                                float prev = -INFINITY;                       // column -1 is padding
+#pragma unroll
+                                for (int ox = 0; ox < 16; ++ox) {
+                                    const float a = rp[(2 * ox) * st.src_C], b = rp[(2 * ox + 1) * st.src_C];
+                                    m[ox] = fmaxf(m[ox], fmaxf(prev, fmaxf(a, b)));
+                                    prev = b;
+                                }
+                            }
+                            float* op = dst + (size_t)oy * 16 * st.dst_C + st.dst_off + c;
+#pragma unroll
+                            for (int ox = 0; ox < 16; ++ox) op[(size_t)ox * st.dst_C] = m[ox];
+                        }
+                        break;
+                    }
                     for (int t = tid; t < Ho * Wo * st.cout; t += FUSED_THREADS) {
                         const int c = t % st.cout, pix = t / st.cout, oy = pix / Wo, ox = pix - oy * Wo;
                         float m = -INFINITY;
