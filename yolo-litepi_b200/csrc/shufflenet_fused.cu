@@ -684,7 +684,9 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     // CAPACITY of the pass, not from how many ROIs are stacked this time: a ROI's logits do not depend
                     // on what else is in the batch
                     const int rows_cap = (kind == 2 ? GT : 1) * st.H * st.W;
-                    const int rt = rows_cap >= 8 ? 8 : (rows_cap >= 4 ? 4 : (rows_cap >= 2 ? 2 : 1));
+                    // 12 rows (three stacked ROIs of 2x2 pixels): three groups of 4, not 8 + 4 padded to 8
+                    // (only while the tiles still fit the 512 threads: conv5 with its 256 channel groups keeps 8-row groups)
+                    const int rt = (rows_cap == 12 && 3 * ncg <= FUSED_THREADS) ? 4 : (rows_cap >= 8 ? 8 : (rows_cap >= 4 ? 4 : (rows_cap >= 2 ? 2 : 1)));
                     const int tiles = ((rows_cap + rt - 1) / rt) * ncg;
                     int ksl = 0;
                     while (ksl < 3 && (tiles << (ksl + 1)) <= FUSED_THREADS) ++ksl;

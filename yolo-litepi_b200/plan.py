@@ -692,6 +692,15 @@ def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, 
         if st[0] == FS_PW and st[17] > 0:
             rows_p = (G * st[10] * st[11] + 15) // 16 * 16
             astage = max(astage, 2 * rows_p * ((st[8] + 15) // 16 * 16 + 8) * 2)
+    # every fp32 pointwise layer must fit its (row group x 4-channel) tiles into the kernel's 512 compute threads
+    # (mirror of the tiling rule in csrc/shufflenet_fused.cu, case FS_PW)
+    for k, st in enumerate(steps):
+        if st[0] != FS_PW:
+            continue
+        cap = (GT if k >= n_front + n_mid else 1) * st[10] * st[11]
+        ncg = (st[9] + 3) // 4
+        rt = 4 if (cap == 12 and 3 * ncg <= 512) else (8 if cap >= 8 else 4 if cap >= 4 else 2 if cap >= 2 else 1)
+        assert -(-cap // rt) * ncg <= 512, f"fused classifier: step {k} needs {-(-cap // rt) * ncg} tiles"
     # tail: rows = the stacked ROIs.  tail_mma: its pointwise layers on the tensor cores with K split over the warps
     # (csrc pw_layer_mma_ks).  Measured SLOWER than the fp32 path (333 ROIs: 947 vs 797 us at tail_group 2; the fp16
     # staging and the partial-sum buffer shrink the weight stages, and group 3 no longer fits), hence off by default.
