@@ -126,6 +126,8 @@ def test_fails_loudly_without_gpu(v1_paths):
         litepi_b200.B200Detector(*v1_paths)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         litepi_b200.B200Classifier(None, "shufflenetv2", num_classes=49)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        litepi_b200.Evaluator()
 
 
 def test_classifier_arch_errors():
