@@ -37,7 +37,7 @@ extern "C" {
 
 typedef struct lp_ctx lp_ctx;
 
-#define LP_ABI_VERSION 3
+#define LP_ABI_VERSION 4
 
 /* ---- network plan (built on the host from the reference's model.ncnn.param) ---- */
 
@@ -104,6 +104,9 @@ int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int n_bufs,
                 const void* weights_tc, size_t tc_bytes, int max_batch);
 /* 1 = use tcgen05 kernels where an op has wtc_off >= 0 (default), 0 = SIMT only. */
 int lp_set_tensor_core(lp_ctx* ctx, int enable);
+/* 1 = chain consecutive tensor-core conv kernels with programmatic dependent launch (default; env LP_NO_PDL=1
+ * starts with 0). */
+int lp_set_pdl(lp_ctx* ctx, int enable);
 
 /* Fused classifier: the whole ShuffleNetV2 forward inside one persistent CTA per SM, driven by a host-built
  * program (plan.py build_fused_classifier -> FusedProgram; struct FStep in csrc/shufflenet_fused.cu, 18 x int32
@@ -115,12 +118,15 @@ int lp_set_tensor_core(lp_ctx* ctx, int enable);
  * astage_bytes of fp16 activation staging and the middle's weight stages), tail_bytes = extent of the tail's map
  * (behind it tail_astage_bytes of fp16 staging, when its pointwise layers also have fp16 weights).
  * weights16 (device, may be NULL) = split-f16 weights [cout_p8][hi|lo][L] of the middle's pointwise layers
- * (FStep.w16_off), which then run on the tensor cores (mma.sync, Ahi*Bhi + Alo*Bhi + Ahi*Blo in fp32). */
+ * (FStep.w16_off), which then run on the tensor cores (mma.sync, Ahi*Bhi + Alo*Bhi + Ahi*Blo in fp32).
+ * park (device, caller-owned like every other buffer) = lp_sm_count(ctx) x tail_group x park_floats floats. */
 int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_mid, int n_tail,
                              const float* weights, const void* weights16, int tail_group, int in_hw, int n_classes,
                              size_t smem_bytes, size_t back_bytes, size_t astage_bytes, size_t tail_bytes,
-                             size_t tail_astage_bytes, int park_floats, float mean, float stdv);
+                             size_t tail_astage_bytes, int park_floats, float* park, size_t park_bytes,
+                             float mean, float stdv);
 int lp_set_fused_classifier(lp_ctx* ctx, int enable);
+int lp_sm_count(lp_ctx* ctx);
 
 /* ---- K1: letterbox.  Replaces letterbox() + cvtColor (e2e.py:66-86, :224-225).
  * frames[i]: HWC BGR u8 image i (pitch[i] bytes per row).  out: B x S x S x 3 RGB u8,
@@ -210,6 +216,12 @@ size_t lp_workspace_bytes(lp_ctx* ctx, int net);
  * disables).  lp_probe_read returns how many samples it wrote (ms each, oldest first, <= 512). */
 int lp_probe_set(lp_ctx* ctx, int net, int op_index);
 int lp_probe_read(lp_ctx* ctx, float* ms_h, int cap);
+
+/* Which kernel family ran each op of plan `net` in the last forward (host array, one int8 per op): 0 generic SIMT
+ * kernel, 1 parameter-weight small-channel conv, 2 tcgen05 implicit-GEMM conv, 3 absorbed by the previous op's
+ * kernel.  Returns the number of entries written.  With lp_probe_set(net, -2) every op gets one event pair
+ * (slot = op index; for the detector slot n_ops is the Detect tail). */
+int lp_op_paths(lp_ctx* ctx, int net, int8_t* out_h, int cap);
 
 /* Debugging: per-role cycle counters of the tensor-core conv kernel (CTA 0) into a device buffer of
  * 16 int64 (NULL disables): [0..2] loader wait-empty/issue/wait-copy, [3..7] MMA wait-acc/wait-patch/

@@ -238,12 +238,12 @@ class DetectorOracle:
     float RGB tensor [B,3,640,640] in [0,1] to ``out0`` [B,5,8400]
     (rows cx,cy,w,h,score in letterbox pixels; e2e.py:244-253 consumes it)."""
 
-    def __init__(self, param_path: str, bin_path: Optional[str] = None, seed: int = 0):
+    def __init__(self, param_path: str, bin_path: Optional[str] = None, seed: int = 0, in_size: int = 640):
         self.layers = parse_param(param_path)
         if bin_path is not None:
             load_bin(self.layers, bin_path)
         else:
-            random_init(self.layers, seed)
+            random_init(self.layers, seed, in_size)
 
     def forward(self, x, want=None):
         if isinstance(x, np.ndarray):

@@ -75,3 +75,34 @@ def load_eval_case(name: str):
         a += pn[i]; b += gn[i]
     want = {k.split(".out.")[1]: d[k] for k in d.files if k.startswith(name + ".out.")}
     return preds, gts, int(d[f"{name}.in.num_classes"]), want
+
+
+def make_variant_param(src_param: str, dst_param: str, nc: int = 1, in_size: int = 640) -> str:
+    """Rewrite the reference's model.ncnn.param into a variant of the same graph family with ``nc`` classes and/or
+    another input size: the three class-logit convs (1x1, cout 1 -> nc), the per-level reshapes, the 64|nc slice and
+    the anchor-count constants (6400/1600/400/8400 at 640).  The product reads only the Convolution records; the
+    graph oracle executes every line, so both see the same architecture."""
+    import re
+    sizes = [(in_size // s) ** 2 for s in (8, 16, 32)]
+    a_old, a_new = 8400, sum(sizes)
+    out = []
+    with open(src_param) as f:
+        lines = f.read().splitlines()
+    for ln in lines:
+        tok = ln.split()
+        if tok and tok[0] == "Convolution" and "0=1" in tok and "1=1" in tok and "5=1" in tok:
+            cin = int([t for t in tok if t.startswith("6=")][0][2:])
+            ln = re.sub(r"\b0=1\b", f"0={nc}", ln, count=1)
+            ln = re.sub(r"\b6=%d\b" % cin, f"6={cin * nc}", ln)
+        elif tok and tok[0] == "Reshape":
+            for old, new in zip((6400, 1600, 400), sizes):
+                ln = re.sub(r"\b0=%d 1=65\b" % old, f"0={new} 1={64 + nc}", ln)
+            ln = re.sub(r"\b0=%d\b" % a_old, f"0={a_new}", ln)
+        elif tok and tok[0] == "Slice" and "-23300=2,64,1" in ln:
+            ln = ln.replace("-23300=2,64,1", f"-23300=2,64,{nc}")
+        elif tok and tok[0] == "MemoryData":
+            ln = re.sub(r"\b0=%d\b" % a_old, f"0={a_new}", ln)
+        out.append(ln)
+    with open(dst_param, "w") as f:
+        f.write("\n".join(out) + "\n")
+    return dst_param

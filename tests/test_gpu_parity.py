@@ -83,13 +83,51 @@ def test_detector_forward_v1_vs_oracle_and_golden(det_v1):
     ref = orc.forward(torch.from_numpy(lbs.astype(np.float32) / 255).permute(0, 3, 1, 2).contiguous()).numpy()
     d = np.abs(got - ref)
     assert d[:, :4].max() < BOX_TOL and d[:, 4].max() < SCORE_TOL
-    if det.model.convs[0].weight is not None and det_v1[0].plan.meta["widths"][0] == 8:
-        g = np.load(os.path.join(GOLDEN, "detector_path.npz"))
-        from helpers import model_paths
-        if model_paths("vntsr")[1] is not None:              # trained weights: compare with the recorded reference run
-            for i, name in enumerate(["vn0", "vn1", "tt0"]):
-                dg = np.abs(got[i] - g[f"{name}.out0"])
-                assert dg[:4].max() < BOX_TOL and dg[4].max() < SCORE_TOL
+
+
+def test_detector_forward_v1_vs_recorded_reference_run(det_v1):
+    """The independent check: out0 of the reference's own graph + TRAINED weights as recorded by
+    tests/golden/make_golden.py (OpenCV-DNN on yolo_plus.onnx).  Needs the trained model.ncnn.bin."""
+    det, _ = det_v1
+    from litepi_b200 import synth
+    from helpers import model_paths
+    if model_paths("vntsr")[1] is None:
+        pytest.skip("trained v1 weights (model.ncnn.bin) are neither mounted nor staged under oracle/_ref: "
+                    "the goldens were recorded with them")
+    g = np.load(os.path.join(GOLDEN, "detector_path.npz"))
+    frames = [synth.vn_frame(0), synth.vn_frame(1), synth.tt_frame(0)]
+    lbs = np.stack([PR.letterbox_ref(f)[0][:, :, ::-1] for f in frames])
+    got = det.forward(lbs)
+    for i, name in enumerate(["vn0", "vn1", "tt0"]):
+        dg = np.abs(got[i] - g[f"{name}.out0"])
+        assert dg[:4].max() < BOX_TOL and dg[4].max() < SCORE_TOL
+
+
+@pytest.mark.parametrize("nc,size", [(3, 640), (1, 320), (5, 416)])
+def test_detector_other_class_counts_and_input_sizes(lp, v1_paths, tmp_path, nc, size):
+    """SURVEY 8(f)4 / ADVICE: the Detect tail takes its geometry (input size, anchors, nc) from the plan.  A variant
+    of the reference graph with nc classes and another input size (random weights) must match the graph oracle,
+    and decode + NMS must stay bit-exact on its multi-class out0."""
+    from helpers import make_variant_param
+    p = make_variant_param(v1_paths[0], str(tmp_path / f"nc{nc}_{size}.param"), nc=nc, in_size=size)
+    det = lp.B200Detector(p, None, input_size=size, max_batch=2, max_det=4096, seed=11)
+    orc = DetectorOracle(p, None, seed=11, in_size=size)
+    _sync(orc, det.model)
+    assert det.nc == nc and det.n_anchors == sum((size // s) ** 2 for s in (8, 16, 32))
+    x = np.random.default_rng(nc * 1000 + size).integers(0, 256, (2, size, size, 3), dtype=np.uint8)
+    got = det.forward(x)
+    ref = orc.forward(torch.from_numpy(x.astype(np.float32) / 255).permute(0, 3, 1, 2).contiguous()).numpy()
+    assert got.shape == ref.shape == (2, 4 + nc, det.n_anchors)
+    d = np.abs(got - ref)
+    assert d[:, :4].max() < BOX_TOL and d[:, 4:].max() < SCORE_TOL
+    # post-processing on the GPU's own out0 (identical input to both sides): bit-exact incl. per-class NMS groups
+    thr = float(np.quantile(got[0, 4:].max(0), 0.97))
+    _check_post(det, got[0], (size, size), 1.0, (0.0, 0.0), thr, 0.45)
+
+
+def test_input_size_must_be_multiple_of_32(lp, v1_paths):
+    with pytest.raises(ValueError):
+        lp.B200Detector(v1_paths[0], None, input_size=500, max_batch=1)
 
 
 def test_detector_forward_v2_random_weights(lp, v2_paths):
@@ -250,6 +288,28 @@ def test_classifier_logits_and_top1(clf):
     assert probs.dtype == np.float32 and probs.shape == (150, 49)
     e = c.predict_batch([])
     assert e[0].shape == (0,) and e[1].shape == (0,)
+
+
+def test_more_than_16_contexts_keep_classifiers_alive(lp):
+    """the fused-classifier state used to live in a 16-slot global table indexed by a wrapping counter, so
+    the 17th context overwrote (and freed the park buffer of) a live classifier.  It now lives in the context."""
+    ref = PR.build_shufflenet(49, seed=8)
+    x = np.random.default_rng(8).integers(0, 256, (5, 64, 64, 3), dtype=np.uint8)
+    first = lp.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=ref.state_dict(), max_batch=8)
+    want = first.logits_for(x)
+    keep = []
+    for i in range(20):
+        other = PR.build_shufflenet(49, seed=100 + i)
+        c = lp.B200Classifier(None, "shufflenetv2", num_classes=49, state_dict=other.state_dict(), max_batch=8,
+                              fused=(i % 3 != 0))
+        c.logits_for(x)
+        keep.append(c)
+        if i % 5 == 4:
+            keep.pop(0)                       # destroy some while others stay alive
+    assert np.array_equal(first.logits_for(x), want)
+    with torch.no_grad():
+        rl = ref((torch.from_numpy(x.astype(np.float32)) / 255 - 0.18).div(0.34).permute(0, 3, 1, 2)).numpy()
+    assert np.abs(want - rl).max() < LOGIT_TOL
 
 
 @pytest.mark.parametrize("mode", ["fused", "layered_tc", "layered_simt"])
@@ -531,3 +591,48 @@ def test_async_step_api_equals_synchronous(lp, v1_paths, clf):
     blank = lp.detector.FrameBatch.from_host([np.full((480, 640, 3), 90, np.uint8)] * 2, pipe.device)
     pipe.enqueue_device(blank, 0.25, 0.45, 50, slot=0); pipe.enqueue_fetch(0)
     assert pipe.collect(0).shape == (0, 9)
+
+
+def test_stream_api_equals_run_batch(lp, v1_paths, clf):
+    """B200Pipeline.stream() / run_stream (pinned ring, copy stream, two lanes, one CUDA graph per step) returns, batch by
+    batch, exactly what the synchronous run_batch returns: for frames produced in place in the pinned ring, for
+    ordinary pageable numpy frames, for pinned torch tensors, with a short last batch, and on graph replays."""
+    from litepi_b200 import synth
+    _, ref = clf
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, max_batch=4,
+                           classifier_state_dict=ref.state_dict(), seed=0)
+    frames = [synth.vn_frame(i) for i in range(22)]
+    batches = [frames[i:i + 4] for i in range(0, 22, 4)]            # 5 full batches + one of 2
+    want = [pipe.run_batch(b, 0.25, 0.45, 50) for b in batches]
+    strip = lambda res: [[(d["bbox"], d["det_class"], d["cls_class"], d["det_conf"], d["cls_conf"]) for d in fr] for fr in res]
+    # (1) public generator API on pageable frames, twice (second pass replays the captured graphs)
+    for _ in range(2):
+        got = list(pipe.run_stream(batches, 0.25, 0.45, 50, lanes=2))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert strip(g) == strip(w)
+    sr = pipe._stream_runner
+    assert sr.graph_failed is None, sr.graph_failed
+    assert sr.steps_graph >= 8 and sr.steps_direct >= 2              # full batches replay graphs, the short one launches directly
+    # (2) frames produced in place in the pinned ring + explicit global frame ids
+    recs = []
+    def produce():
+        for s, b in enumerate(batches[:5]):
+            buf = sr.host_buffer(s, 681, 1198)
+            for i, f in enumerate(b):
+                buf[i] = f
+            yield buf
+    ids = [[100 * s + i for i in range(4)] for s in range(5)]
+    for s, rec in enumerate(sr.run_stream(produce(), 0.25, 0.45, 50, frame_ids=ids)):
+        local = rec.copy(); local[:, 0] -= 100 * s
+        assert strip(pipe.records_to_results(local, 4)) == strip(want[s])
+        assert set(rec[:, 0].tolist()) <= set(ids[s])
+    # (3) pinned torch tensors are read by the copy engine directly
+    pinned = [torch.from_numpy(np.stack(b)).pin_memory() for b in batches[:3]]
+    for s, rec in enumerate(sr.run_stream(pinned, 0.25, 0.45, 50)):
+        assert strip(pipe.records_to_results(rec, 4)) == strip(want[s])
+    # (4) the synchronous latency path
+    one = sr.run_one(batches[1], 0.25, 0.45, 50)
+    assert strip(pipe.records_to_results(one, 4)) == strip(want[1])
+    with pytest.raises(ValueError):
+        list(sr.run_stream([frames[:5]], 0.25, 0.45, 50))           # more than max_batch

@@ -16,7 +16,7 @@ OP_STEM_U8, OP_CONV, OP_DWCONV3, OP_MAXPOOL, OP_UPSAMPLE2, OP_COPY, OP_MEAN_FC =
 ACT_NONE, ACT_SILU, ACT_RELU = range(3)
 FMT_SPLIT16, FMT_F32, FMT_U8 = range(3)
 NET_DETECTOR, NET_CLASSIFIER = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class BufDesc(C.Structure):
@@ -45,9 +45,12 @@ _PROTOS = {
                               C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "lp_set_tensor_core": (C.c_int, [C.c_void_p, C.c_int]),
     "lp_set_fused_classifier": (C.c_int, [C.c_void_p, C.c_int]),
+    "lp_set_pdl": (C.c_int, [C.c_void_p, C.c_int]),
+    "lp_op_paths": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "lp_fused_classifier_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
-                                           C.c_int, C.c_float, C.c_float]),
+                                           C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_float]),
+    "lp_sm_count": (C.c_int, [C.c_void_p]),
     "lp_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "lp_letterbox": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_void_p,
@@ -131,6 +134,16 @@ class Context:
 
     def set_tensor_core(self, enable: bool):
         check(lib().lp_set_tensor_core(self._h, 1 if enable else 0))
+
+    def op_paths(self, net: int):
+        buf = (C.c_int8 * 512)()
+        n = lib().lp_op_paths(self._h, net, buf, 512)
+        if n < 0:
+            check(n, "lp_op_paths")
+        return [int(buf[i]) for i in range(n)]
+
+    def set_pdl(self, enable: bool):
+        check(lib().lp_set_pdl(self._h, 1 if enable else 0))
 
     def close(self):
         if self._h:

@@ -82,12 +82,16 @@ class B200Classifier:
                 self.fused_steps = torch.from_numpy(prog.steps).to(self.device)
                 self.fused_weights = torch.from_numpy(prog.weights).to(self.device)
                 self.fused_weights16 = torch.from_numpy(prog.weights16.view(np.int16)).to(self.device)
+                n_sm = int(L.lib().lp_sm_count(self.ctx.handle))
+                self.fused_park = torch.empty(n_sm * prog.tail_group * prog.park_floats, dtype=torch.float32, device=self.device)
             L.check(L.lib().lp_fused_classifier_load(self.ctx.handle, _ptr(self.fused_steps), prog.n_front, prog.n_mid,
                                                      prog.n_tail, _ptr(self.fused_weights), _ptr(self.fused_weights16),
                                                      prog.tail_group, self.input_size, self.num_classes, prog.smem_bytes,
                                                      prog.back_bytes, prog.astage_bytes, prog.tail_bytes, prog.tail_astage_bytes,
-                                                     prog.park_floats,
+                                                     prog.park_floats, _ptr(self.fused_park), self.fused_park.numel() * 4,
                                                      0.18, 0.34), "lp_fused_classifier_load")
+        else:
+            L.check(L.lib().lp_set_fused_classifier(self.ctx.handle, 0), "lp_set_fused_classifier")
         self._cap = 0
         self._alloc(self.max_batch)
 

@@ -28,14 +28,11 @@ extern "C" int lp_create(lp_ctx** out, int device) {
         return -3;
     }
     LP_CHECK(device >= 0 && device < n, "lp_create: device %d out of range (%d devices)", device, n);
-    LP_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
+    cudaDeviceProp prop;                 // the caller's current device is left alone
     LP_CUDA(cudaGetDeviceProperties(&prop, device));
     LP_CHECK(prop.major == 10, "lp_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
              prop.major, prop.minor);
     lp_ctx* c = new lp_ctx();
-    static int next_slot = 0;
-    c->fused_slot = next_slot++ % 16;
     c->device = device;
     { const char* e = getenv("LP_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
     c->sm_count = prop.multiProcessorCount;
@@ -44,7 +41,10 @@ extern "C" int lp_create(lp_ctx** out, int device) {
 }
 
 extern "C" int lp_destroy(lp_ctx* ctx) {
-    if (ctx) for (cudaEvent_t e : ctx->probe_ev) cudaEventDestroy(e);
+    if (ctx) {
+        for (cudaEvent_t e : ctx->probe_ev) cudaEventDestroy(e);
+        lp_fused_free(ctx->fused);
+    }
     delete ctx;
     return 0;
 }
@@ -82,12 +82,27 @@ extern "C" int lp_set_fused_classifier(lp_ctx* ctx, int enable) {
     return 0;
 }
 
+extern "C" int lp_op_paths(lp_ctx* ctx, int net, int8_t* out_h, int cap) {
+    LP_CHECK(ctx && out_h && (net == 0 || net == 1), "lp_op_paths: bad argument");
+    const lp_net_plan& P = ctx->nets[net];
+    int n = 0;
+    for (; n < (int)P.last_path.size() && n < cap; ++n) out_h[n] = P.last_path[n];
+    return n;
+}
+
+extern "C" int lp_set_pdl(lp_ctx* ctx, int enable) {
+    LP_CHECK(ctx, "lp_set_pdl: null ctx");
+    ctx->use_pdl = enable ? 1 : 0;
+    return 0;
+}
+
 extern "C" int lp_set_tensor_core(lp_ctx* ctx, int enable) {
     LP_CHECK(ctx, "lp_set_tensor_core: null ctx");
     ctx->use_tc = enable ? 1 : 0;
     return 0;
 }
 
+extern "C" int lp_sm_count(lp_ctx* ctx) { return ctx ? ctx->sm_count : -1; }
 extern "C" int64_t lp_launch_count(lp_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 extern "C" size_t lp_workspace_bytes(lp_ctx* ctx, int net) {
@@ -99,6 +114,7 @@ extern "C" int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int 
                            int n_ops, const float* weights, size_t n_floats, const void* weights_tc, size_t tc_bytes,
                            int max_batch) {
     LP_CHECK(ctx && bufs_h && ops_h && weights, "lp_net_load: null argument");
+    lp_device_guard dev_guard(ctx);
     LP_CHECK(net == LP_NET_DETECTOR || net == LP_NET_CLASSIFIER, "lp_net_load: bad net id %d", net);
     LP_CHECK(n_bufs > 0 && n_ops > 0 && max_batch > 0, "lp_net_load: empty plan");
     lp_net_plan& P = ctx->nets[net];
@@ -152,6 +168,7 @@ extern "C" int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int 
 extern "C" int lp_detect_forward(lp_ctx* ctx, const uint8_t* in, int batch, void* workspace, size_t workspace_bytes,
                                  float* out0, void* stream) {
     LP_CHECK(ctx && in && workspace && out0, "lp_detect_forward: null argument");
+    lp_device_guard dev_guard(ctx);
     lp_net_plan& P = ctx->nets[LP_NET_DETECTOR];
     LP_CHECK(P.loaded, "lp_detect_forward: detector not loaded");
     cudaStream_t st = (cudaStream_t)stream;
@@ -159,10 +176,22 @@ extern "C" int lp_detect_forward(lp_ctx* ctx, const uint8_t* in, int batch, void
     if (r) return r;
     const lp_buf_desc& hb = P.bufs.back();
     LP_CHECK(hb.fmt == LP_FMT_F32 && hb.w == 1, "lp_detect_forward: last plan buffer is not the Detect head");
-    if (batch < P.max_batch) {
-        // head rows of image i live at i * image_bytes: contiguous for any batch <= max_batch
+    // geometry from the plan: input size = the u8 image buffer of the stem, nc = width of the class-logit convs
+    // (the ops that write the head buffer at channel 64), anchors = rows of the head buffer
+    const int in_size = P.bufs[P.ops[0].in_buf].h;
+    int nc = 0;
+    for (const lp_op_desc& o : P.ops)
+        if (o.kind == LP_OP_CONV && o.out_buf == (int)P.bufs.size() - 1 && o.out_coff == 64) nc = o.cout_real > 0 ? o.cout_real : o.cout;
+    LP_CHECK(nc >= 1 && hb.c >= 64 + nc, "lp_detect_forward: head buffer has %d channels for nc=%d", hb.c, nc);
+    const int tail_slot = (int)P.ops.size();
+    const bool probe_tail = ctx->probe_net == LP_NET_DETECTOR && ctx->probe_op == -2 && !ctx->probe_ev.empty() && tail_slot < LP_PROBE_RING;
+    if (probe_tail) LP_CUDA(cudaEventRecord(ctx->probe_ev[2 * tail_slot], st));
+    r = lp_launch_detect_tail(ctx, (const float*)((uint8_t*)workspace + hb.offset), batch, hb.c, in_size, nc, hb.h, out0, st);
+    if (probe_tail) {                                  // probe slot n_ops = the Detect tail (bench.py stage table)
+        LP_CUDA(cudaEventRecord(ctx->probe_ev[2 * tail_slot + 1], st));
+        if (ctx->probe_n < tail_slot + 1) ctx->probe_n = tail_slot + 1;
     }
-    return lp_launch_detect_tail(ctx, (const float*)((uint8_t*)workspace + hb.offset), batch, hb.c, out0, st);
+    return r;
 }
 
 extern "C" int lp_set_roi_mode(lp_ctx* ctx, int mode) {
@@ -180,6 +209,7 @@ extern "C" int lp_set_roi_count_device(lp_ctx* ctx, const int32_t* n_rois_dev) {
 extern "C" int lp_classify(lp_ctx* ctx, const uint8_t* in, int n, void* workspace, size_t workspace_bytes,
                            float* logits, float* probs, int64_t* argmax, void* stream) {
     LP_CHECK(ctx && workspace && logits && probs && argmax, "lp_classify: null argument");
+    lp_device_guard dev_guard(ctx);
     if (n == 0) return 0;
     LP_CHECK(in != nullptr, "lp_classify: null input");
     lp_net_plan& P = ctx->nets[LP_NET_CLASSIFIER];

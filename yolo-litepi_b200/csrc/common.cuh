@@ -51,7 +51,12 @@ struct lp_net_plan {
     bool loaded = false;
     std::vector<int> small_slot;    // per op: >= 0 if the small-channel conv path (weights as kernel parameters) covers it
     std::vector<std::vector<float>> small_host;   // per op: host copy [weights | bias] for those ops
+    std::vector<int8_t> last_path;  // per op, which kernel family ran it last (lp_op_paths): 0 generic SIMT, 1 parameter-weight
+                                    // small conv, 2 tcgen05 conv, 3 absorbed by the previous op's kernel
 };
+
+struct lp_fused_cls;                // fused ShuffleNetV2 program of a context (shufflenet_fused.cu)
+void lp_fused_free(lp_fused_cls* f);
 
 struct lp_ctx {
     int device = 0;
@@ -63,7 +68,8 @@ struct lp_ctx {
     int probe_net = -1, probe_op = -1;
     std::vector<cudaEvent_t> probe_ev;   // pairs (start, stop), ring
     int probe_n = 0;
-    int fused_slot = -1;             // index into the fused-classifier table (shufflenet_fused.cu)
+    lp_fused_cls* fused = nullptr;   // owned: fused-classifier program (lp_fused_classifier_load), freed by lp_destroy
+    int attr_set = 0;                // bit per kernel family whose dynamic shared-memory opt-in was made on ctx->device
     int use_fused = 1;
     int use_pdl = 1;                 // programmatic dependent launch between tensor-core conv kernels (env LP_NO_PDL=1 disables)
     int roi_mode = 0;                // 0: e2e.py ROI rules + Pillow resize; 1: e2e_optimize.py rules + cv2 INTER_LINEAR
@@ -71,6 +77,15 @@ struct lp_ctx {
     long long* tc_dbg = nullptr;     // device buffer (16 x int64) for conv_tc role timing; debugging only
 };
 #define LP_PROBE_RING 512
+
+// Entry points run on the context's device whatever the caller's current device is, and restore it on return.
+struct lp_device_guard {
+    int prev = -1;
+    explicit lp_device_guard(const lp_ctx* c) {
+        if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) cudaSetDevice(c->device); else prev = -1;
+    }
+    ~lp_device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // ---- OpenCV 8-bit INTER_LINEAR coefficient of output index d (11-bit fixed point; see preprocess.cu)
 __device__ __forceinline__ void lin_coef(int d, double scale, int n, bool clamp_coef, int& s, int& c0, int& c1) {
@@ -99,7 +114,8 @@ __device__ __forceinline__ void split_make(float v, __half& hi, __half& lo) {
 // kernels implemented per translation unit (host launchers)
 int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, void* workspace,
                 size_t workspace_bytes, float* logits_or_head, cudaStream_t st);
-int lp_launch_detect_tail(lp_ctx* ctx, const float* head_raw, int batch, int head_c, float* out0, cudaStream_t st);
+int lp_launch_detect_tail(lp_ctx* ctx, const float* head_raw, int batch, int head_c, int in_size, int nc, int n_anchors,
+                          float* out0, cudaStream_t st);
 
 // tensor-core path (conv_tc.cu); returns 1 if it handled the op, 0 if not applicable, <0 on error
 int lp_assign_small_slots(lp_net_plan& net, cudaStream_t st);

@@ -729,7 +729,9 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
              workspace_bytes, net.workspace_bytes);
     uint8_t* ws = (uint8_t*)workspace;
     const int net_id = (&net == &ctx->nets[0]) ? 0 : 1;
+    if (net.last_path.size() != net.ops.size()) net.last_path.assign(net.ops.size(), 0);
     for (size_t oi = 0; oi < net.ops.size(); ++oi) {
+        net.last_path[oi] = 0;
         const lp_op_desc& op = net.ops[oi];
         // probe_op >= 0: ring of samples of that op; probe_op == -2: one sample of EVERY op (slot = op index)
         const bool probe_all = (ctx->probe_net == net_id && ctx->probe_op == -2 && !ctx->probe_ev.empty() && (int)oi < LP_PROBE_RING);
@@ -796,7 +798,8 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             const bool ran = small_dispatch(op.ksize, op.stride, op.cin, op.cout, op.kind == LP_OP_STEM_U8, sl);
             if (ran) {
                 LP_LAUNCH_OK(ctx);
-                if (post_slot >= 0) ++oi;            // the 1x1 conv is done
+                net.last_path[oi] = 1;
+                if (post_slot >= 0) { ++oi; net.last_path[oi] = 3; }   // the 1x1 conv is done
                 continue;
             }
             LP_CHECK(post_slot < 0, "small conv dispatch failed after a fusion decision");
@@ -815,7 +818,7 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             if (ctx->use_tc && op.wtc_off >= 0 && net.weights_tc) {
                 int r = lp_conv_tc_try(ctx, net, op, batch, ws, st);
                 if (r < 0) return r;
-                if (r == 1) { ctx->launches++; continue; }
+                if (r == 1) { ctx->launches++; net.last_path[oi] = 2; continue; }
             }
             if (op.ksize == 1) { LP_CHECK(op.stride == 1, "1x1 conv must have stride 1"); launch_conv<1, 1>(p, st); }
             else if (op.ksize == 3 && op.stride == 1) launch_conv<3, 1>(p, st);
@@ -842,6 +845,7 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                 };
                 if (chained(op, o1) && chained(o1, o2) && o2.out_coff - o1.out_coff == step && step >= op.cout) {
                     sppf3_kernel<<<batch * (p.cout / 8), 256, (size_t)p.H * p.W * 96, st>>>(p, step);
+                    net.last_path[oi + 1] = net.last_path[oi + 2] = 3;
                     oi += 2;                          // the two downstream pools are done
                     break;
                 }

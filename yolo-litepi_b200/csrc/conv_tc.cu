@@ -873,11 +873,10 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         p.magic_per_img = magic_u32(p.tiles_x * p.tiles_y);
         p.magic_tiles_x = magic_u32(p.tiles_x);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_set & 1)) {          // per context (= per device): the opt-in is a per-device function attribute
         LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
+        ctx->attr_set |= 1;
     }
     const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_PLAN"); f = e ? atoi(e) : 0; }

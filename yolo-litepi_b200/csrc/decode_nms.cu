@@ -68,18 +68,22 @@ __global__ void __launch_bounds__(256) detect_tail_kernel(const float* __restric
     }
 }
 
-int lp_launch_detect_tail(lp_ctx* ctx, const float* head_raw, int batch, int head_c, float* out0, cudaStream_t st) {
-    // geometry of the 640-input Detect head: strides 8/16/32 (model.ncnn.param:150, 184-186)
+int lp_launch_detect_tail(lp_ctx* ctx, const float* head_raw, int batch, int head_c, int in_size, int nc, int n_anchors,
+                          float* out0, cudaStream_t st) {
+    // geometry of the Detect head: strides 8/16/32 (model.ncnn.param:150, 184-186) on an in_size x in_size input
     LevelTable lv{};
     lv.n = 3;
-    const int S = 640;
+    const int S = in_size;
+    LP_CHECK(S >= 32 && S % 32 == 0, "detect tail: input size %d is not a positive multiple of 32", S);
     int start = 0;
     for (int i = 0; i < 3; ++i) {
         const int s = 8 << i;
         lv.start[i] = start; lv.gw[i] = S / s; lv.stride[i] = (float)s;
         start += (S / s) * (S / s);
     }
-    const int A = start, nc = 1;
+    const int A = start;
+    LP_CHECK(A == n_anchors, "detect tail: head buffer holds %d anchors, input size %d gives %d", n_anchors, S, A);
+    LP_CHECK(nc >= 1 && head_c >= 64 + nc, "detect tail: %d head channels cannot hold 64 DFL logits + %d classes", head_c, nc);
     const long long threads = (long long)batch * A * 4;
     detect_tail_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(head_raw, batch, A, head_c, nc, lv, out0);
     LP_LAUNCH_OK(ctx);
@@ -255,6 +259,7 @@ extern "C" int lp_decode_nms(lp_ctx* ctx, const float* out0, int nc, int n_ancho
                              size_t scratch_bytes, void* stream) {
     LP_CHECK(ctx && out0 && h_h && w_h && ratio_h && pad_h && boxes && scores && classes && keep_idx && counts && n_cand && scratch,
              "lp_decode_nms: null argument");
+    lp_device_guard dev_guard(ctx);
     LP_CHECK(nc >= 1 && n_anchors >= 1 && n_anchors <= 16384, "lp_decode_nms: nc/n_anchors out of range (anchors <= 16384)");
     LP_CHECK(max_det >= 1, "lp_decode_nms: max_det must be >= 1");
     LP_CHECK(scratch_bytes >= lp_decode_nms_scratch_bytes(batch, n_anchors), "lp_decode_nms: scratch too small");
@@ -262,10 +267,9 @@ extern "C" int lp_decode_nms(lp_ctx* ctx, const float* out0, int nc, int n_ancho
     int cap = 1;
     while (cap < n_anchors) cap <<= 1;
     const size_t smem = (size_t)cap * 8 + cap;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        LP_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    if (!(ctx->attr_set & 2)) {          // per context (= per device): the opt-in is a per-device function attribute
+        LP_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 9));
+        ctx->attr_set |= 2;
     }
     Cand* cands = (Cand*)scratch;
     for (int base = 0; base < batch; base += LP_MAX_TABLE) {
@@ -365,6 +369,7 @@ extern "C" int lp_roi_select(lp_ctx* ctx, const float* boxes, const int32_t* cou
                              const int32_t* w_h, int batch, int min_area, int max_rois, int32_t* roi_xyxy,
                              int32_t* roi_src, int32_t* n_rois, void* stream) {
     LP_CHECK(ctx && boxes && counts && h_h && w_h && roi_xyxy && roi_src && n_rois, "lp_roi_select: null argument");
+    lp_device_guard dev_guard(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     if (batch == 0) { LP_CUDA(cudaMemsetAsync(n_rois, 0, 4, st)); return 0; }
     for (int base = 0; base < batch; base += LP_MAX_TABLE) {
@@ -405,6 +410,7 @@ extern "C" int lp_pack_records(lp_ctx* ctx, const int32_t* roi_src, const int32_
                                const float* scores, const int64_t* classes, int max_det, const int64_t* cls_argmax,
                                const float* probs, int n_classes, int n_rois, int32_t* records, void* stream) {
     LP_CHECK(ctx && roi_src && boxes && scores && classes && cls_argmax && probs && records, "lp_pack_records: null argument");
+    lp_device_guard dev_guard(ctx);
     if (n_rois <= 0) return 0;
     pack_records_kernel<<<(n_rois + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         roi_src, frame_ids, boxes, scores, (const long long*)classes, max_det, (const long long*)cls_argmax, probs,

@@ -70,6 +70,7 @@ extern "C" int lp_eval_match(lp_ctx* ctx, const double* pred_box, const int32_t*
                              const double* gt_box, const int32_t* gt_cls, const int32_t* gt_off, int n_frames,
                              int max_per_frame, const double* thresholds, int n_thr, uint8_t* correct, void* stream) {
     LP_CHECK(ctx && pred_off && gt_off && thresholds && n_thr > 0, "lp_eval_match: null argument");
+    lp_device_guard dev_guard(ctx);
     if (n_frames <= 0) return 0;
     LP_CHECK(pred_box && pred_cls && gt_box && gt_cls && correct, "lp_eval_match: null array");
     const size_t smem = (size_t)max_per_frame * sizeof(int);

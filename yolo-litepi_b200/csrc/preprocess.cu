@@ -115,6 +115,7 @@ extern "C" int lp_letterbox(lp_ctx* ctx, const uint8_t* const* frames_h, const i
                             const int64_t* pitch_h, int batch, int out_size, uint8_t* out, double* ratio_h,
                             double* pad_h, void* stream) {
     LP_CHECK(ctx && frames_h && h_h && w_h && out, "lp_letterbox: null argument");
+    lp_device_guard dev_guard(ctx);
     LP_CHECK(batch >= 0 && out_size > 0 && out_size % 4 == 0, "lp_letterbox: bad batch/out_size");
     cudaStream_t st = (cudaStream_t)stream;
     for (int base = 0; base < batch; base += LP_MAX_TABLE) {

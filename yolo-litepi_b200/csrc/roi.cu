@@ -186,6 +186,7 @@ extern "C" int lp_roi_resize(lp_ctx* ctx, const uint8_t* const* frames_h, const 
                              const int32_t* roi_xyxy, const int32_t* roi_src, int n_rois, int out_size,
                              int max_side, uint8_t* out, void* stream) {
     LP_CHECK(ctx && frames_h && pitch_h && roi_xyxy && roi_src && out, "lp_roi_resize: null argument");
+    lp_device_guard dev_guard(ctx);
     LP_CHECK(out_size > 0 && out_size <= 128 && max_side > 0, "lp_roi_resize: bad out_size/max_side");
     if (n_rois <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -206,10 +207,9 @@ extern "C" int lp_roi_resize(lp_ctx* ctx, const uint8_t* const* frames_h, const 
     int tmp_rows = 3 * kmax > 96 ? 3 * kmax : 96;
     size_t smem = (size_t)(2 * out_size * kmax + 4 * out_size + 4) * 4 + (size_t)tmp_rows * out_size * 3;
     LP_CHECK(smem <= 200 * 1024, "lp_roi_resize: max_side %d needs %zu B shared memory", max_side, smem);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        LP_CUDA(cudaFuncSetAttribute(roi_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    if (!(ctx->attr_set & 4)) {          // per context (= per device): the opt-in is a per-device function attribute
+        LP_CUDA(cudaFuncSetAttribute(roi_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->attr_set |= 4;
     }
     for (int base = 0; base < batch; base += LP_MAX_TABLE) {
         const int n = batch - base < LP_MAX_TABLE ? batch - base : LP_MAX_TABLE;

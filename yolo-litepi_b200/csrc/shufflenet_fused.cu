@@ -854,24 +854,28 @@ struct lp_fused_cls {
     float mean = 0.f, stdv = 1.f;
     bool loaded = false;
 };
-static lp_fused_cls g_fused[16];       // one slot per context id (contexts are few and long-lived)
+void lp_fused_free(lp_fused_cls* f) { delete f; }     // owns no device memory: weights, steps and the park buffer are the caller's
 
 extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int n_front, int n_mid, int n_tail,
                                         const float* weights, const void* weights16, int tail_group, int in_hw, int n_classes,
                                         size_t smem_bytes, size_t back_bytes, size_t astage_bytes, size_t tail_bytes,
-                                        size_t tail_astage_bytes, int park_floats, float mean, float stdv) {
-    LP_CHECK(ctx && steps_dev && weights, "lp_fused_classifier_load: null argument");
+                                        size_t tail_astage_bytes, int park_floats, float* park, size_t park_bytes,
+                                        float mean, float stdv) {
+    LP_CHECK(ctx && steps_dev && weights && park, "lp_fused_classifier_load: null argument");
+    lp_device_guard dev_guard(ctx);
     LP_CHECK(n_front + n_mid + n_tail <= FUSED_MAX_STEPS && n_front > 0 && n_mid > 0 && n_tail > 0,
              "lp_fused_classifier_load: bad step counts");
     LP_CHECK(tail_group >= 1 && tail_group <= 8 && park_floats > 0 && park_floats % 4 == 0, "lp_fused_classifier_load: bad tail group");
     LP_CHECK(smem_bytes <= 227 * 1024, "lp_fused_classifier_load: %zu B shared memory exceeds 227 KB", smem_bytes);
-    LP_CHECK(ctx->fused_slot >= 0 && ctx->fused_slot < 16, "lp_fused_classifier_load: too many contexts");
-    lp_fused_cls& f = g_fused[ctx->fused_slot];
+    LP_CHECK(park_bytes >= (size_t)ctx->sm_count * tail_group * park_floats * sizeof(float),
+             "lp_fused_classifier_load: park buffer of %zu B < %d SMs x %d ROIs x %d floats", park_bytes, ctx->sm_count, tail_group, park_floats);
+    if (!ctx->fused) ctx->fused = new lp_fused_cls();
+    lp_fused_cls& f = *ctx->fused;
+    f.loaded = false;
     f.steps_dev = (const FStep*)steps_dev; f.weights = weights; f.weights16 = (const uint4*)weights16;
     f.n_front = n_front; f.n_mid = n_mid; f.n_tail = n_tail; f.GT = tail_group;
     f.in_hw = in_hw; f.n_classes = n_classes; f.mean = mean; f.stdv = stdv;
-    if (f.park) { cudaFree(f.park); f.park = nullptr; }
-    LP_CUDA(cudaMalloc(&f.park, (size_t)ctx->sm_count * tail_group * park_floats * sizeof(float)));
+    f.park = park;
     // the host-built map covers the activations; the two weight stages are appended here
     f.wbuf_off = (int)((smem_bytes + 15) / 16 * 4);
     f.smem_bytes = (size_t)f.wbuf_off * 4 + 2 * WBUF_FLOATS * 4;
@@ -906,8 +910,8 @@ extern "C" int lp_fused_classifier_load(lp_ctx* ctx, const void* steps_dev, int 
 
 // returns 1 if it ran, 0 if no fused classifier is loaded
 int lp_fused_classify(lp_ctx* ctx, const uint8_t* in, int n, float* logits, cudaStream_t st) {
-    if (ctx->fused_slot < 0 || ctx->fused_slot >= 16 || !g_fused[ctx->fused_slot].loaded || !ctx->use_fused) return 0;
-    const lp_fused_cls& f = g_fused[ctx->fused_slot];
+    if (!ctx->fused || !ctx->fused->loaded || !ctx->use_fused) return 0;
+    const lp_fused_cls& f = *ctx->fused;
     const int groups = n;
     const int cs = f.cluster;
     int grid = groups < ctx->sm_count ? groups : ctx->sm_count;

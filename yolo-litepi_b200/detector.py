@@ -70,6 +70,8 @@ class B200Detector:
         # use_gpu / num_threads / input_name / output_name are accepted for signature parity with
         # NCNNDetector (e2e.py:198-200) and ignored: there is one device path.
         self.input_size = int(input_size)
+        if self.input_size < 32 or self.input_size % 32:
+            raise ValueError(f"input_size must be a positive multiple of 32 (Detect strides 8/16/32), got {input_size}")
         self.input_name, self.output_name = input_name, output_name
         if not torch.cuda.is_available():
             raise RuntimeError("litepi_b200: no CUDA device; the B200 backend has no CPU fallback")

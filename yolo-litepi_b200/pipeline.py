@@ -53,6 +53,12 @@ class B200Pipeline:
                  device: int = 0, max_batch: int = 64, max_det: int = 1024, max_rois: Optional[int] = None,
                  classifier_state_dict: Optional[dict] = None, seed: Optional[int] = None,
                  roi_mode: str = "reference"):
+        self._ctor = dict(detector_param=detector_param, detector_bin=detector_bin, classifier_path=classifier_path,
+                          classifier_arch=classifier_arch, num_classes=num_classes, det_input_size=det_input_size,
+                          cls_input_size=cls_input_size, use_gpu_detector=use_gpu_detector,
+                          detector_threads=detector_threads, classifier_device=classifier_device, batch_size=batch_size,
+                          device=device, max_batch=max_batch, max_det=max_det, max_rois=max_rois, seed=seed,
+                          roi_mode=roi_mode)
         self.detector = B200Detector(detector_param, detector_bin, input_size=det_input_size,
                                      use_gpu=use_gpu_detector, num_threads=detector_threads,
                                      device=device, max_batch=max_batch, max_det=max_det, seed=seed or 0)
@@ -78,6 +84,7 @@ class B200Pipeline:
             def __init__(s, a, b): s.a, s.b = a, b
             def launch_count(s): return s.a.launch_count() + s.b.launch_count()
         self.counters = _Launches(self.detector.ctx, self.classifier.ctx)
+        self._stream_runner = None
         self.max_rois = int(max_rois) if max_rois else self.max_batch * 64
         with torch.cuda.device(self.device):
             R = self.max_rois
@@ -130,11 +137,45 @@ class B200Pipeline:
             raise RuntimeError(f"litepi_b200: a frame has more than max_det={self.detector.max_det} detections")
         return n
 
-    def enqueue_fetch(self, slot: int = 0) -> None:
-        """Queue the D2H copy of the step's records (capacity-sized: the count is not known on the host yet)
-        behind the step on the current stream; ``collect(slot)`` waits for it."""
+    def enqueue_fetch_copy(self, slot: int = 0) -> None:
+        """The D2H copy of the step's records (capacity-sized: the count is not known on the host yet), queued
+        behind the step on the current stream.  Capturable in a CUDA graph; ``mark_fetch`` records its event."""
         self._records_h[slot].copy_(self.records, non_blocking=True)
+
+    def mark_fetch(self, slot: int = 0) -> None:
         self._fetched[slot].record(torch.cuda.current_stream())
+
+    def mark_enqueued(self, slot: int, n_frames: int) -> None:
+        """Host-side bookkeeping of ``enqueue_device`` when the step was replayed from a CUDA graph."""
+        self._pending[slot] = int(n_frames)
+
+    def enqueue_fetch(self, slot: int = 0) -> None:
+        self.enqueue_fetch_copy(slot)
+        self.mark_fetch(slot)
+
+    def clone(self) -> "B200Pipeline":
+        """A second instance with the same models and its own workspace (one per lane of ``stream()``)."""
+        return B200Pipeline(**self._ctor, classifier_state_dict=self.classifier.state_dict)
+
+    def stream(self, lanes: int = 2, use_graph: Optional[bool] = None):
+        """Host-buffer streaming front end (pinned ring, copy stream, lanes, CUDA graph): see stream.py."""
+        from .stream import StreamRunner
+        return StreamRunner(self, lanes=lanes, use_graph=use_graph)
+
+    def run_stream(self, batches, conf_threshold: float = 0.5, iou_threshold: float = 0.45, min_area: int = 100,
+                   lanes: int = 2):
+        """Iterate batches of HOST frames (lists / arrays of HWC BGR uint8, e.g. what cv2.imread returns) through the
+        whole hot path; yields one result list per batch (per frame: the dicts of e2e.py:519-529), in order."""
+        if getattr(self, "_stream_runner", None) is None or self._stream_runner.n_lanes != lanes:
+            self._stream_runner = self.stream(lanes)
+        sizes: List[int] = []
+
+        def counted():
+            for b in batches:
+                sizes.append(len(b))
+                yield b
+        for rec in self._stream_runner.run_stream(counted(), conf_threshold, iou_threshold, min_area):
+            yield self.records_to_results(rec, sizes.pop(0))
 
     def collect(self, slot: int = 0) -> np.ndarray:
         """Records of the step enqueued with ``slot`` (after ``enqueue_fetch``), as a [n, 9] int32 array."""
