@@ -146,13 +146,14 @@ def random_init(layers: List[Layer], seed: int = 0, in_size: int = 640) -> None:
 
 @torch.no_grad()
 def run_graph(layers: List[Layer], x: torch.Tensor, want: Optional[List[str]] = None,
-              dtype: torch.dtype = torch.float32, quant=None) -> Dict[str, torch.Tensor]:
+              dtype: torch.dtype = torch.float32, quant=None, quant_for=None) -> Dict[str, torch.Tensor]:
     """Execute the graph on ``x`` [B,3,H,W]; returns {blob name: tensor}.
 
     Tensors carry a leading batch dim; ncnn axis k maps to torch dim k+1.
     ``want`` = blob names to keep (default: just the last layer's outputs).
     ``quant`` = optional f(tensor)->tensor applied to every conv's input and
-    weights (precision-budget experiments, oracle/experiments/precision.py).
+    weights (precision-budget experiments, oracle/experiments/precision.py); ``quant_for`` = optional
+    f(layer name) -> (activation rounding, weight rounding) for a per-layer budget (precision_budget.py).
     """
     blobs: Dict[str, torch.Tensor] = {}
     keep = set(want or [])
@@ -173,6 +174,9 @@ def run_graph(layers: List[Layer], x: torch.Tensor, want: Optional[List[str]] = 
                 squeeze = True
             if quant is not None and L.bias is not None:       # not the DFL projection
                 a, w = quant(a), quant(w)
+            if quant_for is not None and L.bias is not None:
+                qa, qw = quant_for(L.name)
+                a, w = qa(a), qw(w)
             y = F.conv2d(a, w, b, stride=(p.get(13, p.get(3, 1)), p.get(3, 1)),
                          padding=(p.get(14, p.get(4, 0)), p.get(4, 0)),
                          dilation=(p.get(12, p.get(2, 1)), p.get(2, 1)))

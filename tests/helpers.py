@@ -95,8 +95,8 @@ def make_variant_param(src_param: str, dst_param: str, nc: int = 1, in_size: int
             ln = re.sub(r"\b0=1\b", f"0={nc}", ln, count=1)
             ln = re.sub(r"\b6=%d\b" % cin, f"6={cin * nc}", ln)
         elif tok and tok[0] == "Reshape":
-            for old, new in zip((6400, 1600, 400), sizes):
-                ln = re.sub(r"\b0=%d 1=65\b" % old, f"0={new} 1={64 + nc}", ln)
+            lvl = dict(zip(("6400", "1600", "400"), sizes))
+            ln = re.sub(r"\b0=(6400|1600|400) 1=65\b", lambda m: f"0={lvl[m.group(1)]} 1={64 + nc}", ln)   # one pass: 6400->1600 must not cascade
             ln = re.sub(r"\b0=%d\b" % a_old, f"0={a_new}", ln)
         elif tok and tok[0] == "Slice" and "-23300=2,64,1" in ln:
             ln = ln.replace("-23300=2,64,1", f"-23300=2,64,{nc}")
