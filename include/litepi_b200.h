@@ -37,21 +37,26 @@ extern "C" {
 
 typedef struct lp_ctx lp_ctx;
 
-#define LP_ABI_VERSION 4
+#define LP_ABI_VERSION 5
 
 /* ---- network plan (built on the host from the reference's model.ncnn.param) ---- */
 
 enum lp_op_kind {
-    LP_OP_STEM_U8   = 0,  /* conv 3x3 s2 on the u8 letterboxed/ROI image, x/255 (and optional mean/std) fused */
+    LP_OP_STEM_U8   = 0,  /* conv kxk (3x3 s2; 7x7 s2 for ResNet) on the u8 letterboxed/ROI image, x/255 (and optional mean/std) fused */
     LP_OP_CONV      = 1,  /* conv kxk (k in {1,3}), stride 1|2, bias, act, optional residual add */
-    LP_OP_DWCONV3   = 2,  /* depthwise 3x3 stride 1|2, bias, no act (ShuffleNetV2 branches) */
+    LP_OP_DWCONV3   = 2,  /* depthwise k x k (3; 5 in EfficientNet) stride 1|2, bias, act (none in ShuffleNetV2, ReLU6 / SiLU in MobileNetV2 / EfficientNet) */
     LP_OP_MAXPOOL   = 3,  /* max pool k x k, stride s, pad k/2 (SPPF 5/1, ShuffleNetV2 3/2) */
     LP_OP_UPSAMPLE2 = 4,  /* nearest x2 (model.10 / model.13, model.ncnn.param:88,103) */
     LP_OP_COPY      = 5,  /* channel-slice copy (ShuffleNetV2 pass-through half) */
-    LP_OP_MEAN_FC   = 6   /* global mean over HxW + FC (torchvision shufflenetv2.py forward tail) */
+    LP_OP_MEAN_FC   = 6,  /* global mean over HxW + FC (torchvision shufflenetv2.py forward tail) */
+    LP_OP_GLOBAL_MEAN = 7, /* [H,W,C] -> [1,1,C] mean (SqueezeExcitation.avgpool, torchvision ops/misc.py) */
+    LP_OP_SCALE     = 8   /* out = in * gate, gate = the [1,1,C] map in res_buf (SqueezeExcitation scale) */
 };
 
-enum lp_act { LP_ACT_NONE = 0, LP_ACT_SILU = 1, LP_ACT_RELU = 2 };
+enum lp_act { LP_ACT_NONE = 0, LP_ACT_SILU = 1, LP_ACT_RELU = 2, LP_ACT_RELU6 = 3 /* MobileNetV2 */, LP_ACT_SIGMOID = 4 };
+/* lp_op_desc.flags */
+#define LP_OPF_RES_BEFORE_ACT 1   /* out = act(conv + bias + residual): torchvision BasicBlock (resnet.py forward); default is
+                                     act(conv + bias) + residual, the Ultralytics Bottleneck / C2f shortcut */
 enum lp_fmt { LP_FMT_SPLIT16 = 0, LP_FMT_F32 = 1, LP_FMT_U8 = 2 };
 
 /* One NHWC activation buffer inside the caller-provided workspace. */
@@ -79,6 +84,7 @@ typedef struct lp_op_desc {
     int32_t res_buf, res_coff;          /* residual added AFTER the activation (-1 = none) */
     int32_t ksize, stride, act;
     int32_t row_off;                    /* Detect head: first anchor row this level writes */
+    int32_t flags;                      /* LP_OPF_* */
     float   in_mean, in_std;            /* STEM_U8: x = (u8/255 - in_mean)/in_std (detector: 0, 1) */
     int64_t w_off, b_off;               /* offsets (in floats) into the fp32 weight blob:
                                            weights [tap][cin][cout], bias [cout] */

@@ -249,6 +249,38 @@ def build_shufflenet(num_classes: int, seed: int = 0):
     return m
 
 
+def build_classifier_ref(arch: str, num_classes: int, seed: int = 0):
+    """e2e.py:320-335 ``build_classifier`` for every ``--clf_arch`` the reference accepts (resnet18, efficientnet = b0,
+    mobilenetv2, shufflenetv2), random-init under ``torch.manual_seed(seed)`` with seeded non-trivial BatchNorm
+    statistics (so that BN folding in the product is exercised)."""
+    import torch
+    import torch.nn as nn
+    from torchvision import models
+    torch.manual_seed(seed)
+    if arch == "resnet18":
+        m = models.resnet18(weights=None)
+        m.fc = nn.Linear(m.fc.in_features, num_classes)
+    elif arch == "efficientnet":
+        m = models.efficientnet_b0(weights=None)
+        m.classifier[1] = nn.Linear(m.classifier[1].in_features, num_classes)
+    elif arch == "mobilenetv2":
+        m = models.mobilenet_v2(weights=None)
+        m.classifier[1] = nn.Linear(m.classifier[1].in_features, num_classes)
+    elif arch == "shufflenetv2":
+        return build_shufflenet(num_classes, seed)
+    else:
+        raise ValueError(f"Unknown architecture: {arch}")
+    g = torch.Generator().manual_seed(seed + 1)
+    for mod in m.modules():
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.weight.data = 0.8 + 0.4 * torch.rand(mod.weight.shape, generator=g)
+            mod.bias.data = 0.1 * torch.randn(mod.bias.shape, generator=g)
+            mod.running_mean.data = 0.1 * torch.randn(mod.running_mean.shape, generator=g)
+            mod.running_var.data = 0.8 + 0.4 * torch.rand(mod.running_var.shape, generator=g)
+    m.eval()
+    return m
+
+
 def classify_ref(model, rois_bgr: List[np.ndarray], size: int = 64):
     """e2e.py:378-396 -- returns (argmax int64 [B], probs f32 [B,C], logits f32 [B,C])."""
     import torch

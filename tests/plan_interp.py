@@ -13,6 +13,18 @@ import torch.nn.functional as F
 from litepi_b200 import _lib as L
 
 
+def _act(y, act):
+    if act == L.ACT_SILU:
+        return y * torch.sigmoid(y)
+    if act == L.ACT_RELU:
+        return torch.relu(y)
+    if act == L.ACT_RELU6:
+        return torch.clamp(y, 0.0, 6.0)
+    if act == L.ACT_SIGMOID:
+        return torch.sigmoid(y)
+    return y
+
+
 def run_plan_cpu(plan, x_u8: np.ndarray):
     """x_u8: [B,S,S,3] RGB uint8.  Returns (buffers list, logits or None)."""
     B = x_u8.shape[0]
@@ -32,16 +44,20 @@ def run_plan_cpu(plan, x_u8: np.ndarray):
             w = W[op["w_off"]:op["w_off"] + k * k * cin * cout].reshape(k, k, cin, cout).permute(3, 2, 0, 1)
             b = W[op["b_off"]:op["b_off"] + cout]
             y = F.conv2d(xin.permute(0, 3, 1, 2), w, b, stride=s, padding=k // 2).permute(0, 2, 3, 1)
-            if op["act"] == L.ACT_SILU:
-                y = y * torch.sigmoid(y)
-            elif op["act"] == L.ACT_RELU:
-                y = torch.relu(y)
-            if op["res_buf"] >= 0:
+            res_first = bool(op.get("flags", 0) & L.OPF_RES_BEFORE_ACT)
+            if op["res_buf"] >= 0 and res_first:
+                y = y + bufs[op["res_buf"]][..., op["res_coff"]:op["res_coff"] + cout]
+            y = _act(y, op["act"])
+            if op["res_buf"] >= 0 and not res_first:
                 y = y + bufs[op["res_buf"]][..., op["res_coff"]:op["res_coff"] + cout]
         elif kind == L.OP_DWCONV3:
-            w = W[op["w_off"]:op["w_off"] + 9 * cout].reshape(3, 3, cout).permute(2, 0, 1).unsqueeze(1)
+            w = W[op["w_off"]:op["w_off"] + k * k * cout].reshape(k, k, cout).permute(2, 0, 1).unsqueeze(1)
             b = W[op["b_off"]:op["b_off"] + cout]
-            y = F.conv2d(xin.permute(0, 3, 1, 2), w, b, stride=s, padding=1, groups=cout).permute(0, 2, 3, 1)
+            y = _act(F.conv2d(xin.permute(0, 3, 1, 2), w, b, stride=s, padding=k // 2, groups=cout).permute(0, 2, 3, 1), op["act"])
+        elif kind == L.OP_GLOBAL_MEAN:
+            y = xin.mean(dim=(1, 2), keepdim=True)
+        elif kind == L.OP_SCALE:
+            y = xin * bufs[op["res_buf"]][..., op["res_coff"]:op["res_coff"] + cout]
         elif kind == L.OP_MAXPOOL:
             y = F.max_pool2d(xin.permute(0, 3, 1, 2), k, s, k // 2).permute(0, 2, 3, 1)
         elif kind == L.OP_UPSAMPLE2:

@@ -636,3 +636,40 @@ def test_stream_api_equals_run_batch(lp, v1_paths, clf):
     assert strip(pipe.records_to_results(one, 4)) == strip(want[1])
     with pytest.raises(ValueError):
         list(sr.run_stream([frames[:5]], 0.25, 0.45, 50))           # more than max_batch
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "mobilenetv2", "efficientnet"])
+def test_other_classifier_archs(lp, v1_paths, arch):
+    """the reference's other --clf_arch choices (build_classifier, e2e.py:322-335) on the GPU: logits within
+    1e-2 of torchvision, top-1 equal, predict_batch contract; and the whole pipeline with that classifier against the oracle."""
+    from litepi_b200 import synth
+    ref = PR.build_classifier_ref(arch, 49, seed=3)
+    c = lp.B200Classifier(None, arch, num_classes=49, state_dict=ref.state_dict(), max_batch=64)
+    assert not c.fused
+    crops = synth.roi_crops(70, seed=11)                        # 70 > max_batch: two chunks
+    u8 = np.stack([PR.classifier_input_ref(cr)[0] for cr in crops])
+    lg = c.logits_for(u8)
+    with torch.no_grad():
+        rl = ref(((torch.from_numpy(u8.astype(np.float32)) / 255 - 0.18) / 0.34).permute(0, 3, 1, 2)).numpy()
+    assert np.abs(lg - rl).max() < LOGIT_TOL
+    assert np.array_equal(lg.argmax(1), rl.argmax(1))
+    cls, probs = c.predict_batch(crops)
+    assert np.array_equal(cls, rl.argmax(1)) and probs.shape == (70, 49) and np.allclose(probs.sum(1), 1.0, atol=1e-5)
+    if arch == "resnet18":
+        pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, arch, num_classes=49, max_batch=2,
+                               classifier_state_dict=ref.state_dict(), seed=0)
+        orc = DetectorOracle(v1_paths[0], v1_paths[1], seed=0)
+        _sync(orc, pipe.detector.model)
+        frames = [synth.vn_frame(i) for i in range(3)]
+        got = pipe.run_batch(frames, 0.25, 0.45, 50)
+        for f, g in zip(frames, got):
+            rois_want = oracle_pipeline_run(orc, ref, f, 0.25, 0.45, 50)
+            _compare(g, rois_want)
+        streamed = list(pipe.run_stream([frames[:2], frames[2:]], 0.25, 0.45, 50))
+        assert [[d["bbox"] for d in fr] for b in streamed for fr in b] == [[d["bbox"] for d in fr] for fr in got]
+        assert [[d["cls_class"] for d in fr] for b in streamed for fr in b] == [[d["cls_class"] for d in fr] for fr in got]
+
+
+def test_unknown_classifier_arch_raises(lp):
+    with pytest.raises(ValueError):
+        lp.B200Classifier(None, "vgg16", num_classes=49)

@@ -219,3 +219,24 @@ def test_eval_host_metrics_equal_reference_golden():
         got = metrics_from_stats(np.concatenate(cs), np.concatenate(conf), np.concatenate(pcs), np.concatenate(tcs), nc)
         for k, v in want.items():
             assert np.array_equal(np.asarray(got[k]), v), (case, k)
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "mobilenetv2", "efficientnet"])
+def test_other_classifier_archs_plan_equals_torchvision(arch):
+    """the layer plans of the reference's other --clf_arch choices (e2e.py:322-335), executed by the CPU
+    plan interpreter with the CUDA executor's buffer / channel-padding / residual semantics, reproduce torchvision."""
+    import torch
+    from litepi_b200.cls_archs import PLAN_BUILDERS
+    from oracle import pipeline_ref as PR
+    ref = PR.build_classifier_ref(arch, 49, seed=3)
+    plan = PLAN_BUILDERS[arch](ref.state_dict(), 64)
+    assert plan.meta["num_classes"] == 49
+    x = np.random.default_rng(5).integers(0, 256, (3, 64, 64, 3), dtype=np.uint8)
+    _, logits = run_plan_cpu(plan, x)
+    with torch.no_grad():
+        want = ref(((torch.from_numpy(x.astype(np.float32)) / 255 - 0.18) / 0.34).permute(0, 3, 1, 2)).numpy()
+    assert np.abs(logits.numpy() - want).max() < 2e-4 * max(1.0, np.abs(want).max())
+    assert np.array_equal(logits.numpy().argmax(1), want.argmax(1))
+    plan.layout(4)
+    tc = plan.pack_tc_weights()
+    assert tc.size > 0 and sum(1 for o in plan.ops if o["wtc_off"] >= 0) > 5      # most convs are tensor-core eligible

@@ -12,11 +12,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblitepi_b200.so")
 
 # enums (include/litepi_b200.h)
-OP_STEM_U8, OP_CONV, OP_DWCONV3, OP_MAXPOOL, OP_UPSAMPLE2, OP_COPY, OP_MEAN_FC = range(7)
-ACT_NONE, ACT_SILU, ACT_RELU = range(3)
+OP_STEM_U8, OP_CONV, OP_DWCONV3, OP_MAXPOOL, OP_UPSAMPLE2, OP_COPY, OP_MEAN_FC, OP_GLOBAL_MEAN, OP_SCALE = range(9)
+ACT_NONE, ACT_SILU, ACT_RELU, ACT_RELU6, ACT_SIGMOID = range(5)
+OPF_RES_BEFORE_ACT = 1
 FMT_SPLIT16, FMT_F32, FMT_U8 = range(3)
 NET_DETECTOR, NET_CLASSIFIER = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class BufDesc(C.Structure):
@@ -30,7 +31,7 @@ class OpDesc(C.Structure):
                 ("out_cstride", C.c_int32), ("cout_real", C.c_int32), ("out_seg_len", C.c_int32),
                 ("out_seg_pad", C.c_int32), ("res_buf", C.c_int32), ("res_coff", C.c_int32),
                 ("ksize", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32),
-                ("row_off", C.c_int32), ("in_mean", C.c_float), ("in_std", C.c_float),
+                ("row_off", C.c_int32), ("flags", C.c_int32), ("in_mean", C.c_float), ("in_std", C.c_float),
                 ("w_off", C.c_int64), ("b_off", C.c_int64), ("wtc_off", C.c_int64)]
 
 

@@ -15,16 +15,13 @@ from .detector import FrameBatch, _ptr, _stream
 from .plan import build_classifier_plan, build_fused_classifier
 
 
-def _random_state_dict(num_classes: int, seed: Optional[int]):
-    """The reference builds ``models.shufflenet_v2_x1_0(weights=None)`` and swaps ``fc``
-    (e2e.py:331-333); a missing weight file silently keeps that random init (e2e.py:337-343)."""
-    import torch.nn as nn
-    from torchvision import models
+def _random_state_dict(num_classes: int, seed: Optional[int], arch: str = "shufflenetv2"):
+    """The reference builds the torchvision model with ``weights=None`` and swaps the classification head
+    (e2e.py:322-333); a missing weight file silently keeps that random init (e2e.py:337-343)."""
+    from .cls_archs import torchvision_model
     if seed is not None:
         torch.manual_seed(seed)
-    m = models.shufflenet_v2_x1_0(weights=None)
-    m.fc = nn.Linear(m.fc.in_features, num_classes)
-    return m.state_dict()
+    return torchvision_model(arch, num_classes).state_dict()
 
 
 class B200Classifier:
@@ -33,9 +30,9 @@ class B200Classifier:
                  cuda_device: int = 0, max_batch: int = 256, seed: Optional[int] = None,
                  tensor_cores: bool = True, fused: bool = True, fused_group: int = 3):
         # `device` is the reference's torch device string (e2e.py:354); this backend always runs on
-        # cuda:`cuda_device`.  Only shufflenetv2 is implemented (ValueError like e2e.py:335 otherwise).
-        if arch != "shufflenetv2":
-            raise ValueError(f"Unknown architecture: {arch} (the B200 backend implements shufflenetv2)")
+        # cuda:`cuda_device`.  The four architectures of build_classifier (e2e.py:322-335); ValueError like :335 otherwise.
+        if arch not in ("shufflenetv2", "resnet18", "mobilenetv2", "efficientnet"):
+            raise ValueError(f"Unknown architecture: {arch}")
         if not torch.cuda.is_available():
             raise RuntimeError("litepi_b200: no CUDA device; the B200 backend has no CPU fallback")
         self.arch, self.num_classes, self.input_size = arch, int(num_classes), int(input_size)
@@ -43,19 +40,23 @@ class B200Classifier:
         self.ctx = L.Context(cuda_device)         # one lp_ctx per classifier object
         sd = state_dict
         if sd is None:
-            sd = _random_state_dict(self.num_classes, seed)
+            sd = _random_state_dict(self.num_classes, seed, arch)
             if model_path and os.path.exists(model_path):
                 try:
                     loaded = torch.load(model_path, map_location="cpu")
                     ref = {k: v.shape for k, v in sd.items()}
                     if set(loaded) != set(ref) or any(tuple(loaded[k].shape) != tuple(ref[k]) for k in ref):
-                        raise RuntimeError("state_dict does not match shufflenet_v2_x1_0")
+                        raise RuntimeError(f"state_dict does not match the torchvision {arch} model")
                     sd = loaded
                     print(f"✓ Loaded classifier weights from {model_path}")
                 except Exception as e:                                   # e2e.py:342-343
                     print(f"⚠ Warning: Could not load weights: {e}")
         self.state_dict = sd
-        self.plan = build_classifier_plan(sd, self.input_size)
+        if arch == "shufflenetv2":
+            self.plan = build_classifier_plan(sd, self.input_size)
+        else:
+            from .cls_archs import PLAN_BUILDERS
+            self.plan = PLAN_BUILDERS[arch](sd, self.input_size)
         if self.plan.meta["num_classes"] != self.num_classes:
             raise ValueError("state_dict fc size does not match num_classes")
         self.max_batch = int(max_batch)
@@ -74,7 +75,7 @@ class B200Classifier:
                     "lp_net_load(classifier)")
         # the production path: the whole network in one persistent kernel (csrc/shufflenet_fused.cu); the
         # layer-by-layer plan above stays loaded as the cross-check (set_fused(False))
-        self.fused = self._has_fused = bool(fused) and self.input_size == 64
+        self.fused = self._has_fused = bool(fused) and self.input_size == 64 and arch == "shufflenetv2"
         if self.fused:
             prog = build_fused_classifier(sd, in_size=self.input_size, tail_group=fused_group,
                                           tail_mma=os.environ.get("LP_CLS_TAIL_MMA", "0") == "1")

@@ -152,7 +152,7 @@ extern "C" int lp_net_load(lp_ctx* ctx, int net, const lp_buf_desc* bufs_h, int 
             }
         }
         const size_t wn = o.kind == LP_OP_CONV || o.kind == LP_OP_STEM_U8 ? (size_t)o.ksize * o.ksize * o.cin * o.cout
-                          : o.kind == LP_OP_DWCONV3 ? (size_t)9 * o.cout
+                          : o.kind == LP_OP_DWCONV3 ? (size_t)o.ksize * o.ksize * o.cout
                           : o.kind == LP_OP_MEAN_FC ? (size_t)o.cin * o.cout : 0;
         if (wn) LP_CHECK(o.w_off >= 0 && (size_t)o.w_off + wn <= n_floats && o.b_off >= 0 && (size_t)o.b_off + o.cout <= n_floats,
                          "lp_net_load: op %d weights outside the blob", i);

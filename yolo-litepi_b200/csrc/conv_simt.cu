@@ -22,6 +22,7 @@ struct ConvParams {
     int cout_real, seg_l0, seg_len, seg_pad;   // segmented destination (lp_op_desc.out_seg_len); seg_len == 0: plain
     int H, W, Ho, Wo;        // input / output spatial size
     int ksize, stride, act;
+    int res_first;           // LP_OPF_RES_BEFORE_ACT: act(conv + bias + residual)
     int n_img;
     const float* w;          // [tap][cin][cout]
     const float* bias;       // [cout]
@@ -31,6 +32,8 @@ struct ConvParams {
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == LP_ACT_SILU) return v / (1.f + __expf(-v));
     if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == LP_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+    if (act == LP_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
     return v;
 }
 
@@ -162,12 +165,12 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(ConvParams p) {
         const int ck = min(CK, p.cin - c0);
         // ---- stage input patch
         if (KS == 1) {
-            // flattened pixels: (STRIDE==1 only) input pixel == output pixel
+            // flattened OUTPUT pixels; input pixel = output pixel * STRIDE (1x1 stride 2 = ResNet's downsample branch)
             float v[CK];
 #pragma unroll
             for (int i = 0; i < CK; ++i) v[i] = 0.f;
             if (valid) {
-                long long idx = (long long)img * p.in.img + ((long long)oy * p.W + ox) * p.in.C + p.in.coff + c0;
+                long long idx = (long long)img * p.in.img + ((long long)(oy * STRIDE) * p.W + ox * STRIDE) * p.in.C + p.in.coff + c0;
                 if (ck == CK && p.in.fmt == LP_FMT_SPLIT16) ld8(p.in, idx, v);
                 else for (int i = 0; i < ck; ++i) v[i] = ld_elem(p.in, idx + i);
             }
@@ -236,8 +239,9 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_simt_kernel(ConvParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float x = acc[g * 8 + i] + (i < n ? __ldg(p.bias + cbase + i) : 0.f);
+            if (p.res.base && i < n && p.res_first) x += r[i];
             x = act_apply(x, p.act);
-            if (p.res.base && i < n) x += r[i];
+            if (p.res.base && i < n && !p.res_first) x += r[i];
             v[i] = x;
         }
         if (n == 8 && p.out_cstride == 1 && p.seg_len == 0 && (p.out.fmt == LP_FMT_SPLIT16)) st8(p.out, opix + cbase, v);
@@ -310,6 +314,47 @@ __global__ void __launch_bounds__(CONV_THREADS) stem_u8_kernel(ConvParams p) {
         if (n == 8 && p.out.fmt == LP_FMT_SPLIT16) st8(p.out, opix + cbase, v);
         else for (int i = 0; i < n; ++i) st_elem(p.out, opix + cbase + i, v[i]);
     }
+}
+
+// Any odd kernel size / stride from the u8 image (ResNet18's 7x7 stride-2 conv1, torchvision resnet.py): thread =
+// output pixel x 8 output channels, taps straight from global memory (the image is L1/L2 resident; 9.6 MMAC per ROI).
+__global__ void __launch_bounds__(128) stem_u8_generic_kernel(ConvParams p) {
+    const int groups = (p.cout + 7) / 8;
+    const long long total = (long long)p.n_img * p.Ho * p.Wo * groups;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    long long r = i / groups;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int img = (int)(r / p.Ho);
+    const int pad = p.ksize / 2, c0 = g * 8, n = min(8, p.cout - c0);
+    const uint8_t* src = (const uint8_t*)p.in.base + (long long)img * p.in.img;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int ky = 0; ky < p.ksize; ++ky) {
+        const int iy = oy * p.stride - pad + ky;
+        if (iy < 0 || iy >= p.H) continue;
+        for (int kx = 0; kx < p.ksize; ++kx) {
+            const int ix = ox * p.stride - pad + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            const uint8_t* q = src + ((long long)iy * p.W + ix) * 3;
+            const float* w = p.w + (long long)((ky * p.ksize + kx) * 3) * p.cout + c0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float x = __fdiv_rn((float)q[c], 255.f);
+                if (p.in_scale_std != 1.f || p.in_scale_mean != 0.f) x = __fdiv_rn(__fsub_rn(x, p.in_scale_mean), p.in_scale_std);
+                for (int k = 0; k < n; ++k) acc[k] = fmaf(x, __ldg(w + (long long)c * p.cout + k), acc[k]);
+            }
+        }
+    }
+    const long long opix = (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = act_apply(acc[k] + (k < n ? __ldg(p.bias + c0 + k) : 0.f), p.act);
+    if (n == 8 && p.out.fmt == LP_FMT_SPLIT16) st8(p.out, opix + c0, v);
+    else for (int k = 0; k < n; ++k) st_elem(p.out, opix + c0 + k, v[k]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,20 +535,43 @@ __global__ void dwconv3_kernel(ConvParams p) {
     const int oy = (int)(r % p.Ho);
     const int img = (int)(r / p.Ho);
     float acc = __ldg(p.bias + c);
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int iy = oy * p.stride - 1 + ky;
+    const int K = p.ksize, pad = K / 2;                     // 3 (ShuffleNetV2, MobileNetV2) or 5 (EfficientNet)
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * p.stride - pad + ky;
         if (iy < 0 || iy >= p.H) continue;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int ix = ox * p.stride - 1 + kx;
+        for (int kx = 0; kx < K; ++kx) {
+            const int ix = ox * p.stride - pad + kx;
             if (ix < 0 || ix >= p.W) continue;
             const float a = ld_elem(p.in, (long long)img * p.in.img + ((long long)iy * p.W + ix) * p.in.C + p.in.coff + c);
-            acc = fmaf(a, __ldg(p.w + (ky * 3 + kx) * p.cout + c), acc);
+            acc = fmaf(a, __ldg(p.w + (ky * K + kx) * p.cout + c), acc);
         }
     }
     acc = act_apply(acc, p.act);
     st_elem(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + out_chan(p, c), acc);
+}
+
+// SqueezeExcitation pieces (torchvision ops/misc.py): mean over H x W per channel, and x * gate[c]
+__global__ void global_mean_kernel(ConvParams p) {
+    const long long total = (long long)p.n_img * p.cout;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % p.cout), img = (int)(i / p.cout);
+    float s = 0.f;
+    for (int q = 0; q < p.H * p.W; ++q) s += ld_elem(p.in, (long long)img * p.in.img + (long long)q * p.in.C + p.in.coff + c);
+    st_elem(p.out, (long long)img * p.out.img + p.out.coff + c, s / (float)(p.H * p.W));
+}
+
+__global__ void scale_kernel(ConvParams p) {
+    const long long total = (long long)p.n_img * p.Ho * p.Wo * p.cout;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % p.cout);
+    const long long pix = i / p.cout;
+    const int img = (int)(pix / ((long long)p.Ho * p.Wo));
+    const long long q = pix - (long long)img * p.Ho * p.Wo;
+    const float g = ld_elem(p.res, (long long)img * p.res.img + p.res.coff + c);
+    const float x = ld_elem(p.in, (long long)img * p.in.img + q * p.in.C + p.in.coff + c);
+    st_elem(p.out, (long long)img * p.out.img + q * p.out.C + p.out.coff + c, x * g);
 }
 
 __global__ void maxpool_kernel(ConvParams p) {
@@ -749,6 +817,7 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
         p.cout_real = op.cout_real > 0 ? op.cout_real : op.cout;
         p.seg_len = op.out_seg_len; p.seg_pad = op.out_seg_pad; p.seg_l0 = op.out_seg_len > 0 ? op.out_coff : 0;
         p.ksize = op.ksize; p.stride = op.stride; p.act = op.act; p.n_img = batch;
+        p.res_first = (op.flags & LP_OPF_RES_BEFORE_ACT) ? 1 : 0;
         p.w = net.weights + op.w_off; p.bias = net.weights + op.b_off;
         p.in_scale_mean = 0.f; p.in_scale_std = 1.f;
         if (op.kind == LP_OP_STEM_U8) {
@@ -761,17 +830,18 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             const lp_buf_desc& ib = net.bufs[op.in_buf];
             p.in = make_ref(net, op.in_buf, op.in_coff, ws, 0);
             p.H = ib.h; p.W = ib.w;
-            if (op.kind == LP_OP_CONV) p.res = make_ref(net, op.res_buf, op.res_coff, ws, 0);
+            if (op.kind == LP_OP_CONV || op.kind == LP_OP_SCALE) p.res = make_ref(net, op.res_buf, op.res_coff, ws, 0);
         }
         if (op.kind != LP_OP_MEAN_FC) {
             p.out = make_ref(net, op.out_buf, op.out_seg_len > 0 ? 0 : op.out_coff, ws, op.row_off);
-            p.Ho = (op.kind == LP_OP_UPSAMPLE2) ? p.H * 2 : (op.kind == LP_OP_COPY ? p.H : (p.H + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
-            p.Wo = (op.kind == LP_OP_UPSAMPLE2) ? p.W * 2 : (op.kind == LP_OP_COPY ? p.W : (p.W + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
+            const bool same_hw = op.kind == LP_OP_COPY || op.kind == LP_OP_SCALE;
+            p.Ho = (op.kind == LP_OP_UPSAMPLE2) ? p.H * 2 : op.kind == LP_OP_GLOBAL_MEAN ? 1 : (same_hw ? p.H : (p.H + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
+            p.Wo = (op.kind == LP_OP_UPSAMPLE2) ? p.W * 2 : op.kind == LP_OP_GLOBAL_MEAN ? 1 : (same_hw ? p.W : (p.W + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1);
             if (!(ob.w == 1 && ob.h > 1))     // Detect-head row buffers ([anchors][C]) are addressed through row_off
                 LP_CHECK(ob.h == p.Ho && ob.w == p.Wo, "op %zu: output buffer %dx%d != computed %dx%d", oi, ob.h, ob.w, p.Ho, p.Wo);
         }
         const long long total = (long long)batch * p.Ho * p.Wo * p.cout;
-        if ((op.kind == LP_OP_STEM_U8 || op.kind == LP_OP_CONV) && net.small_slot.size() > oi && net.small_slot[oi] >= 0 &&
+        if ((op.kind == LP_OP_STEM_U8 || op.kind == LP_OP_CONV) && net.small_slot.size() > oi && net.small_slot[oi] >= 0 && op.flags == 0 &&
             (p.res.base == nullptr || (p.res.fmt == LP_FMT_SPLIT16 && p.res.coff % 8 == 0)) && p.seg_len == 0 &&
             p.out_cstride == 1 && p.out.fmt == LP_FMT_SPLIT16 &&
             (op.kind == LP_OP_STEM_U8 || p.in.fmt == LP_FMT_SPLIT16) && p.in.coff % 8 == 0 && p.out.coff % 8 == 0) {
@@ -806,7 +876,12 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
         }
         switch (op.kind) {
         case LP_OP_STEM_U8: {
-            LP_CHECK(op.ksize == 3 && op.stride == 2 && op.cout <= 32, "stem: unsupported shape");
+            if (!(op.ksize == 3 && op.stride == 2 && op.cout <= 32)) {          // ResNet conv1 (7x7 s2, 64 channels) and friends
+                LP_CHECK(op.ksize % 2 == 1 && op.stride >= 1, "stem: kernel size must be odd");
+                const long long threads = (long long)batch * p.Ho * p.Wo * ((op.cout + 7) / 8);
+                stem_u8_generic_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p);
+                break;
+            }
             dim3 grid(((p.Wo + TILE_W - 1) / TILE_W) * ((p.Ho + TILE_H - 1) / TILE_H), 1, batch);
             if (op.cout <= 8) stem_u8_kernel<8><<<grid, CONV_THREADS, 0, st>>>(p);
             else if (op.cout <= 16) stem_u8_kernel<16><<<grid, CONV_THREADS, 0, st>>>(p);
@@ -820,7 +895,8 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                 if (r < 0) return r;
                 if (r == 1) { ctx->launches++; net.last_path[oi] = 2; continue; }
             }
-            if (op.ksize == 1) { LP_CHECK(op.stride == 1, "1x1 conv must have stride 1"); launch_conv<1, 1>(p, st); }
+            if (op.ksize == 1 && op.stride == 1) launch_conv<1, 1>(p, st);
+            else if (op.ksize == 1 && op.stride == 2) launch_conv<1, 2>(p, st);
             else if (op.ksize == 3 && op.stride == 1) launch_conv<3, 1>(p, st);
             else if (op.ksize == 3 && op.stride == 2) launch_conv<3, 2>(p, st);
             else LP_CHECK(false, "conv: unsupported ksize %d stride %d", op.ksize, op.stride);
@@ -863,6 +939,13 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             else resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
             break;
         }
+        case LP_OP_GLOBAL_MEAN:
+            global_mean_kernel<<<(unsigned)(((long long)batch * p.cout + 127) / 128), 128, 0, st>>>(p);
+            break;
+        case LP_OP_SCALE:
+            LP_CHECK(p.res.base != nullptr, "scale: no gate buffer");
+            scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+            break;
         case LP_OP_MEAN_FC:
             LP_CHECK(logits != nullptr, "mean_fc: logits pointer is null");
             mean_fc_kernel<<<batch, 256, op.cin * sizeof(float), st>>>(p, logits);

@@ -63,7 +63,7 @@ struct TcParams {
     const __half* res; long long res_plane, res_img; int res_C, res_coff;
     const uint8_t* wtc;        // packed split weights of this op
     const float* bias;
-    int cin, cout, act;
+    int cin, cout, act, res_first;
     int cout_real, out_cstride, seg_l0, seg_len, seg_pad;   // segmented (channel-shuffle) destination; seg_len == 0: plain
     int H, W, Ho, Wo;          // input / output spatial size
     int n_img, tiles_x, tiles_y, n_tiles;
@@ -658,14 +658,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                     f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + __uint_as_float(v2[4 * q + 2]) + b.z;
                     f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + __uint_as_float(v2[4 * q + 3]) + b.w;
                 }
+                // residual: after the activation (C2f / Bottleneck shortcut) or, with res_first, before it (torchvision BasicBlock)
+                for (int pass = 0; pass < 2; ++pass) {
+                if (pass == (p.res_first ? 1 : 0)) {
                 if (p.act == LP_ACT_SILU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
                 } else if (p.act == LP_ACT_RELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+                } else if (p.act == LP_ACT_RELU6) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = fminf(fmaxf(f[i], 0.f), 6.f);
                 }
-                if (p.res) {
+                } else if (p.res) {
 #pragma unroll
                     for (int h8 = 0; h8 < 2; ++h8) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(p.res + rbase + c0 + 8 * h8);
@@ -679,6 +685,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                             f[8 * h8 + 2 * i + 1] += a.y + b.y;
                         }
                     }
+                }
                 }
                 if (p.out_fmt == LP_FMT_SPLIT16) {
                     uint4 oh[2], ol[2];
@@ -831,7 +838,8 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_DEBUG"); f = e ? atoi(e) : 0; } p.dbg_flags = f; }
     p.wtc = net.weights_tc + op.wtc_off + wtc_off;
     p.bias = net.weights + op.b_off + n0;
-    p.cin = op.cin; p.cout = nb; p.act = op.act;
+    p.cin = op.cin; p.cout = nb; p.act = op.act; p.res_first = (op.flags & LP_OPF_RES_BEFORE_ACT) ? 1 : 0;
+    if (op.act != LP_ACT_NONE && op.act != LP_ACT_SILU && op.act != LP_ACT_RELU && op.act != LP_ACT_RELU6) return 0;
     p.out_cstride = op.out_cstride > 0 ? op.out_cstride : 1;
     p.seg_len = op.out_seg_len; p.seg_pad = op.out_seg_pad;
     p.seg_l0 = seg ? op.out_coff + n0 * p.out_cstride : 0;

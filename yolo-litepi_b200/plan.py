@@ -108,7 +108,7 @@ class Plan:
     # ---- ops
     def conv(self, name: str, w: np.ndarray, b: Optional[np.ndarray], src: View, dst: View, stride: int, act: int,
              res: Optional[View] = None, row_off: int = 0, out_cstride: int = 1, kind: int = L.OP_CONV,
-             in_mean: float = 0.0, in_std: float = 1.0, seg: Optional[Tuple[int, int, int]] = None) -> None:
+             in_mean: float = 0.0, in_std: float = 1.0, seg: Optional[Tuple[int, int, int]] = None, flags: int = 0) -> None:
         """w: [cout, cin, k, k] (logical channels) -> packed [tap][cin_phys][cout_phys], zero padded.
         ``seg`` = (logical offset, segment length, padded segment length): output j goes to LOGICAL channel
         off + j*out_cstride of a buffer whose logical channels are stored in padded segments."""
@@ -137,24 +137,37 @@ class Plan:
                              cout_real=cout if seg else coutp, out_seg_len=seg[1] if seg else 0,
                              out_seg_pad=seg[2] if seg else 0,
                              res_buf=res.buf if res is not None else -1, res_coff=res.start if res is not None else 0,
-                             ksize=k, stride=stride, act=act, row_off=row_off, in_mean=in_mean, in_std=in_std,
+                             ksize=k, stride=stride, act=act, row_off=row_off, flags=flags, in_mean=in_mean, in_std=in_std,
                              w_off=self._push(wp), b_off=self._push(bp), wtc_off=-1))
         self.names.append(name)
         self.macs.append(ho * wo * k * k * cin * cout)
 
     def simple(self, kind: int, name: str, src: View, dst: View, ksize: int = 1, stride: int = 1,
                out_cstride: int = 1, w: Optional[np.ndarray] = None, b: Optional[np.ndarray] = None,
-               act: int = L.ACT_NONE, seg: Optional[Tuple[int, int, int]] = None) -> None:
+               act: int = L.ACT_NONE, seg: Optional[Tuple[int, int, int]] = None, res: Optional[View] = None) -> None:
         n = src.phys if (out_cstride == 1 and seg is None) else src.logical
         w_off = self._push(w) if w is not None else 0
         b_off = self._push(b) if b is not None else 0
         self.ops.append(dict(kind=kind, in_buf=src.buf, in_coff=src.start, cin=n, out_buf=dst.buf,
                              out_coff=seg[0] if seg else dst.start,
                              cout=n, out_cstride=out_cstride, cout_real=n, out_seg_len=seg[1] if seg else 0,
-                             out_seg_pad=seg[2] if seg else 0, res_buf=-1, res_coff=0, ksize=ksize, stride=stride,
-                             act=act, row_off=0, in_mean=0.0, in_std=1.0, w_off=w_off, b_off=b_off, wtc_off=-1))
+                             out_seg_pad=seg[2] if seg else 0, res_buf=res.buf if res is not None else -1,
+                             res_coff=res.start if res is not None else 0, ksize=ksize, stride=stride,
+                             act=act, row_off=0, flags=0, in_mean=0.0, in_std=1.0, w_off=w_off, b_off=b_off, wtc_off=-1))
         self.names.append(name)
         self.macs.append(0)
+
+    def mean_fc(self, src: View, fcw: np.ndarray, fcb: np.ndarray) -> None:
+        """global mean over HxW + Linear (torchvision classifiers' avgpool + flatten + fc); fcw [classes, channels]."""
+        cin_phys = self.bufs[src.buf]["c"]
+        wp = np.zeros((cin_phys, fcw.shape[0]), np.float32)
+        wp[src.chan_map() + src.start] = fcw.T
+        self.ops.append(dict(kind=L.OP_MEAN_FC, in_buf=src.buf, in_coff=0, cin=cin_phys, out_buf=-1, out_coff=0,
+                             cout=fcw.shape[0], out_cstride=1, cout_real=fcw.shape[0], out_seg_len=0, out_seg_pad=0,
+                             res_buf=-1, res_coff=0, ksize=1, stride=1, act=L.ACT_NONE, row_off=0, flags=0,
+                             in_mean=0.0, in_std=1.0, w_off=self._push(wp), b_off=self._push(fcb), wtc_off=-1))
+        self.names.append("mean_fc")
+        self.macs.append(int(fcw.size))
 
     # ---- finalisation
     def layout(self, max_batch: int) -> int:
@@ -482,7 +495,7 @@ def build_classifier_plan(state_dict: dict, in_size: int = 64, mean: float = 0.1
     P.ops.append(dict(kind=L.OP_MEAN_FC, in_buf=y.buf, in_coff=0, cin=fcw.shape[1], out_buf=-1, out_coff=0,
                       cout=fcw.shape[0], out_cstride=1, cout_real=fcw.shape[0], out_seg_len=0, out_seg_pad=0,
                       res_buf=-1, res_coff=0, ksize=1, stride=1, act=NONE,
-                      row_off=0, in_mean=0.0, in_std=1.0, w_off=P._push(fcw.T.copy()), b_off=P._push(fcb), wtc_off=-1))
+                      row_off=0, flags=0, in_mean=0.0, in_std=1.0, w_off=P._push(fcw.T.copy()), b_off=P._push(fcb), wtc_off=-1))
     P.names.append("mean_fc")
     P.macs.append(fcw.size)
     P.meta.update(num_classes=int(fcw.shape[0]), in_size=S)

@@ -188,6 +188,8 @@ class StreamRunner:
                 else:
                     fb = self.fb[b] if n == self.B else FrameBatch([self.dev[b][i] for i in range(n)])
                     pipe.enqueue_device(fb, conf, iou, min_area, self.fid[b], slot=slot)
+                    if not pipe.classifier.fused:          # layer-by-layer classifiers are sized on the host (one sync per step)
+                        pipe.finish(fb, self.fid[b], slot)
                     pipe.enqueue_fetch_copy(slot)
                     self.steps_direct += 1
                 pipe.mark_fetch(slot)
