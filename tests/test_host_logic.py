@@ -131,7 +131,9 @@ def test_fails_loudly_without_gpu(v1_paths):
 
 
 def test_classifier_arch_errors():
-    with pytest.raises(ValueError, match="Unknown architecture"):
+    with pytest.raises(ValueError, match="Unknown architecture"):          # e2e.py:335
+        litepi_b200.B200Classifier(None, "vgg16")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):             # a supported arch still needs the GPU
         litepi_b200.B200Classifier(None, "resnet18")
 
 
