@@ -610,9 +610,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 oimg = (int)q;
                 opin = (int)(gpu - q * (unsigned)hw_out);
             } else {
-                const unsigned img = __umulhi((unsigned)tile, p.magic_per_img);
-                const unsigned rr = (unsigned)tile - img * (unsigned)(p.tiles_x * p.tiles_y);
-                const unsigned ty = __umulhi(rr, p.magic_tiles_x), tx = rr - ty * (unsigned)p.tiles_x;
+                // division by multiply-high; ceil(2^32 / 1) does not fit 32 bits, so a divisor of 1 (maps no larger than one
+                // 16x8 tile: the 8x8 .. 2x2 stages of the classifier backbones) is the identity
+                const unsigned per_img = (unsigned)(p.tiles_x * p.tiles_y);
+                const unsigned img = per_img == 1 ? (unsigned)tile : __umulhi((unsigned)tile, p.magic_per_img);
+                const unsigned rr = (unsigned)tile - img * per_img;
+                const unsigned ty = p.tiles_x == 1 ? rr : __umulhi(rr, p.magic_tiles_x), tx = rr - ty * (unsigned)p.tiles_x;
                 const int oy = (int)ty * TCT_H + (r >> 3), ox = (int)tx * TCT_W + (r & 7);
                 valid = (oy < p.Ho && ox < p.Wo);
                 oimg = (int)img;
@@ -832,7 +835,8 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         const lp_buf_desc& rb = net.bufs[op.res_buf];
         if (rb.fmt != LP_FMT_SPLIT16 || op.res_coff % 8) return 0;
         p.res = reinterpret_cast<const __half*>(ws + rb.offset);
-        p.res_img = rb.image_bytes / 2; p.res_plane = (long long)net.max_batch * p.res_img; p.res_C = rb.c; p.res_coff = op.res_coff;
+        p.res_img = rb.image_bytes / 2; p.res_plane = (long long)net.max_batch * p.res_img; p.res_C = rb.c;
+        p.res_coff = op.res_coff + n0;                // this launch covers output channels [n0, n0 + nb) of the op
     }
     p.dbg = ctx->tc_dbg;
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_DEBUG"); f = e ? atoi(e) : 0; } p.dbg_flags = f; }
