@@ -215,6 +215,24 @@ int lp_eval_match(lp_ctx* ctx, const double* pred_box, const int32_t* pred_cls, 
                   const double* gt_box, const int32_t* gt_cls, const int32_t* gt_off, int n_frames,
                   int max_per_frame, const double* thresholds, int n_thr, uint8_t* correct, void* stream);
 
+/* ---- Frame ingest: baseline JPEG decode on the device.  Replaces cv2.imread (e2e.py:962) for frames
+ * that arrive as JPEG bytes; bit-exact with cv2.imdecode (libjpeg-turbo defaults: islow IDCT, fancy up-sampling).
+ * All images of a call share one header (size, sampling, tables): `desc` (host) + `tables` (device blob of
+ * lp_jpeg_tables_bytes() bytes, layout = struct JpegTables in csrc/jpeg.cu, built by jpeg.py pack_tables).
+ * data (device) = the entropy-coded scans back to back (everything after SOS, stuffing and RSTn markers intact);
+ * img_off (device, batch + 1 int64) = their byte offsets.  frames_out = batch x height x width x 3 BGR u8.
+ * One thread decodes one restart interval, so throughput needs an encoder that emits RSTn every few MCUs. */
+typedef struct lp_jpeg_desc {
+    int32_t width, height, ncomp;       /* ncomp 1 (grey) or 3 (YCbCr) */
+    int32_t h[3], v[3];                 /* sampling factors: luma 1x1 / 2x1 / 2x2, chroma 1x1 */
+    int32_t tq[3], td[3], ta[3];        /* quantisation / DC / AC table selectors per component */
+    int32_t restart_interval;           /* MCUs per restart interval (DRI), 0 = none */
+} lp_jpeg_desc;
+size_t lp_jpeg_tables_bytes(void);
+size_t lp_jpeg_scratch_bytes(const lp_jpeg_desc* desc, int batch);
+int lp_jpeg_decode(lp_ctx* ctx, const uint8_t* data, const int64_t* img_off, int batch, const lp_jpeg_desc* desc,
+                   const void* tables, void* scratch, size_t scratch_bytes, uint8_t* frames_out, void* stream);
+
 /* Workspace bytes lp_detect_forward / lp_classify need for the loaded plan (0 if not loaded). */
 size_t lp_workspace_bytes(lp_ctx* ctx, int net);
 

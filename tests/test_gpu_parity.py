@@ -673,3 +673,75 @@ def test_other_classifier_archs(lp, v1_paths, arch):
 def test_unknown_classifier_arch_raises(lp):
     with pytest.raises(ValueError):
         lp.B200Classifier(None, "vgg16", num_classes=49)
+
+
+# ------------------------------------------------------------------------------------------ frame ingest (JPEG)
+def _jpeg(a, q=90, sf=None, rst=0):
+    import cv2
+    par = [cv2.IMWRITE_JPEG_QUALITY, q]
+    if sf is not None:
+        par += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf]
+    if rst:
+        par += [cv2.IMWRITE_JPEG_RST_INTERVAL, rst]
+    ok, b = cv2.imencode(".jpg", a, par)
+    assert ok
+    return bytes(b)
+
+
+@pytest.mark.parametrize("h,w,q,sf,rst", [(64, 48, 90, None, 0), (37, 53, 75, None, 0), (120, 160, 95, None, 4), (8, 8, 100, None, 0),
+                                          (33, 17, 90, "444", 3), (40, 72, 85, "422", 2), (9, 200, 90, None, 1), (1, 1, 90, None, 0),
+                                          (681, 1198, 90, None, 4), (512, 512, 30, None, 7), (100, 100, 10, None, 0)])
+def test_jpeg_decode_bit_exact_vs_cv2(lp, h, w, q, sf, rst):
+    """device JPEG decode == cv2.imdecode (what the reference's cv2.imread returns, e2e.py:962), bit for bit:
+    sampling 4:2:0 / 4:2:2 / 4:4:4, odd sizes, with and without restart intervals, several qualities, batches."""
+    import cv2
+    from litepi_b200 import _lib as L
+    from litepi_b200.jpeg import JpegBatchDecoder
+    sfv = {None: None, "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422}[sf]
+    rng = np.random.default_rng(h * 7 + w)
+    imgs = []
+    for k in range(3):
+        small = rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8, 3), dtype=np.uint8)
+        a = cv2.resize(small, (w, h), interpolation=cv2.INTER_CUBIC)
+        imgs.append(np.clip(a.astype(np.int16) + rng.integers(-8, 9, a.shape), 0, 255).astype(np.uint8))
+    js = [_jpeg(a, q, sfv, rst) for a in imgs]
+    dec = JpegBatchDecoder(L.context(0), torch.device("cuda", 0), max_batch=4)
+    got = dec.decode(js).cpu().numpy()
+    for k, j in enumerate(js):
+        want = cv2.imdecode(np.frombuffer(j, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(got[k], want), f"image {k}: {int((got[k] != want).sum())} bytes differ"
+
+
+def test_jpeg_grey_and_errors(lp):
+    import cv2
+    from litepi_b200 import _lib as L
+    from litepi_b200.jpeg import JpegBatchDecoder
+    dec = JpegBatchDecoder(L.context(0), torch.device("cuda", 0), max_batch=2)
+    g = np.random.default_rng(1).integers(0, 256, (50, 70), dtype=np.uint8)
+    j = _jpeg(g, 85)
+    assert np.array_equal(dec.decode([j])[0].cpu().numpy(), cv2.imdecode(np.frombuffer(j, np.uint8), cv2.IMREAD_COLOR))
+    a = np.random.default_rng(2).integers(0, 256, (32, 32, 3), dtype=np.uint8)
+    with pytest.raises(ValueError, match="share one header"):
+        dec.decode([_jpeg(a, 90), _jpeg(a, 50)])
+    ok, prog = cv2.imencode(".jpg", a, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(ValueError, match="baseline"):
+        dec.decode([bytes(prog)])
+
+
+def test_stream_from_jpeg_bytes_equals_decoded_frames(lp, v1_paths, clf):
+    """run_stream on JPEG byte strings (decode on the device, only the entropy-coded bytes cross PCIe) returns exactly what
+    run_batch returns on the frames cv2.imdecode produces from the same bytes."""
+    import cv2
+    from litepi_b200 import synth
+    _, ref = clf
+    pipe = lp.B200Pipeline(v1_paths[0], v1_paths[1], None, "shufflenetv2", num_classes=49, max_batch=4,
+                           classifier_state_dict=ref.state_dict(), seed=0)
+    js = [_jpeg(synth.vn_frame(i), 90, None, 4) for i in range(10)]
+    frames = [cv2.imdecode(np.frombuffer(j, np.uint8), cv2.IMREAD_COLOR) for j in js]
+    batches = [js[i:i + 4] for i in range(0, 10, 4)]
+    want = [pipe.run_batch(frames[i:i + 4], 0.25, 0.45, 50) for i in range(0, 10, 4)]
+    strip = lambda res: [[(d["bbox"], d["det_class"], d["cls_class"], d["det_conf"], d["cls_conf"]) for d in fr] for fr in res]
+    for _ in range(2):
+        got = list(pipe.run_stream(batches, 0.25, 0.45, 50))
+        assert [strip(g) for g in got] == [strip(w) for w in want]
+    assert sum(len(fr) for w in want for fr in w) > 10

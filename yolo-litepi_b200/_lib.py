@@ -35,6 +35,11 @@ class OpDesc(C.Structure):
                 ("w_off", C.c_int64), ("b_off", C.c_int64), ("wtc_off", C.c_int64)]
 
 
+class JpegDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32), ("h", C.c_int32 * 3), ("v", C.c_int32 * 3),
+                ("tq", C.c_int32 * 3), ("td", C.c_int32 * 3), ("ta", C.c_int32 * 3), ("restart_interval", C.c_int32)]
+
+
 _lib = None
 
 _PROTOS = {
@@ -74,6 +79,10 @@ _PROTOS = {
     "lp_set_roi_count_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lp_eval_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "lp_jpeg_tables_bytes": (C.c_size_t, []),
+    "lp_jpeg_scratch_bytes": (C.c_size_t, [C.POINTER(JpegDesc), C.c_int]),
+    "lp_jpeg_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(JpegDesc), C.c_void_p, C.c_void_p,
+                                 C.c_size_t, C.c_void_p, C.c_void_p]),
     "lp_launch_count": (C.c_int64, [C.c_void_p]),
     "lp_debug_tc_timing": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lp_probe_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

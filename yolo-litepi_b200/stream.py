@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from .detector import FrameBatch
+from .jpeg import JpegBatchDecoder, is_jpeg
 
 Frames = Union[np.ndarray, Sequence[np.ndarray]]
 
@@ -52,6 +53,10 @@ class StreamRunner:
         self.steps_graph = self.steps_direct = 0
         self.graph_kernels = {}             # kernels inside each captured graph (lp_launch_count delta of its capture)
         self.replayed_kernels = 0
+        # JPEG ingest (frames handed in as encoded bytes): one decoder (tables + scratch) per lane, pinned byte ring
+        self.jpeg = [JpegBatchDecoder(p.ctx, self.device, self.B) for p in self.pipes]
+        self.jcap = 0
+        self.h2d_bytes = 0                  # bytes copied host -> device so far (frames or JPEG scans)
 
     # ------------------------------------------------------------------ buffers
     def _ensure(self, h: int, w: int) -> None:
@@ -72,6 +77,20 @@ class StreamRunner:
         self.graphs = {}
         self.shape = (h, w)
 
+    def _ensure_jpeg(self, need: int) -> None:
+        if need <= self.jcap:
+            return
+        torch.cuda.synchronize(self.device)
+        cap = int(need * 1.25) + 4096
+        with torch.cuda.device(self.device):
+            self.jhost = [torch.empty((cap,), dtype=torch.uint8).pin_memory() for _ in range(self.n_buf)]
+            self.jhost_np = [t.numpy() for t in self.jhost]
+            self.jdev = [torch.empty((cap,), dtype=torch.uint8, device=self.device) for _ in range(self.n_buf)]
+            self.joff_h = [torch.zeros((self.B + 1,), dtype=torch.int64).pin_memory() for _ in range(self.n_buf)]
+            self.joff_np = [t.numpy() for t in self.joff_h]
+            self.joff = [torch.zeros((self.B + 1,), dtype=torch.int64, device=self.device) for _ in range(self.n_buf)]
+        self.jcap = cap
+
     def host_buffer(self, i: int, h: int, w: int) -> np.ndarray:
         """Pinned staging buffer ``i % n_buf`` as a [max_batch, h, w, 3] uint8 array.  Blocks until the copy engine has
         finished reading its previous contents, so a producer may overwrite it."""
@@ -90,6 +109,16 @@ class StreamRunner:
         if n < 1 or n > self.B:
             raise ValueError(f"a batch holds 1..{self.B} frames, got {n}")
         f0 = frames[0]
+        if not isinstance(frames, (np.ndarray, torch.Tensor)) and is_jpeg(f0):
+            # encoded frames: only the entropy-coded bytes cross PCIe, the decode runs on the lane's stream
+            dec = self.jpeg[b % self.n_lanes]
+            hit = dec.header(f0)
+            self._ensure(hit[0].height, hit[0].width)
+            self._ensure_jpeg(sum(len(j) for j in frames))
+            if self.used[b]:
+                self.ready[b].synchronize()
+            hit, used = dec.stage(frames, self.jhost_np[b], self.joff_np[b])
+            return n, ("jpeg", hit, used)
         if isinstance(frames, torch.Tensor):
             if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3 or not frames.is_contiguous():
                 raise ValueError("tensor batches must be contiguous [n,H,W,3] uint8")
@@ -162,16 +191,28 @@ class StreamRunner:
                     self.fid_h[b][:n] = torch.arange(n, dtype=torch.int32)
                 else:
                     self.fid_h[b][:n] = torch.as_tensor(frame_ids, dtype=torch.int32)
+                jpeg = isinstance(src, tuple) and src[0] == "jpeg"
                 with torch.cuda.stream(self.copy_stream):
                     if self.used[b]:
                         self.copy_stream.wait_event(self.consumed[b])
-                    self.dev[b][:n].copy_((self.host[b] if src is None else src)[:n], non_blocking=True)
+                    if jpeg:
+                        used = max(int(src[2]), 1)
+                        self.jdev[b][:used].copy_(self.jhost[b][:used], non_blocking=True)
+                        self.joff[b].copy_(self.joff_h[b], non_blocking=True)
+                        self.h2d_bytes += used + 8 * (self.B + 1)
+                    else:
+                        s_t = (self.host[b] if src is None else src)[:n]
+                        self.dev[b][:n].copy_(s_t, non_blocking=True)
+                        self.h2d_bytes += 0 if s_t.is_cuda else s_t.numel()
                     self.fid[b][:n].copy_(self.fid_h[b][:n], non_blocking=True)
                     self.ready[b].record(self.copy_stream)
                 self.used[b] = True
             with torch.cuda.stream(st):
                 if h2d:
                     st.wait_event(self.ready[b])
+                    if jpeg:                               # JPEG bytes -> BGR frames in the device ring (csrc/jpeg.cu)
+                        import ctypes as _C
+                        self.jpeg[ln].decode_device(src[1], self.jdev[b], self.joff[b], n, self.dev[b], _C.c_void_p(st.cuda_stream))
                 g = None
                 if self.use_graph and n == self.B:
                     key = (float(conf), float(iou), int(min_area))
