@@ -597,6 +597,26 @@ def bench_pipeline(args):
     pageable = np.array(frames, copy=True)
     ms_p, _ = e2e_run((pageable for _ in range(p_steps)), p_steps, [ids_step] * p_steps)
     e2e_pageable = world * B * p_steps / (ms_p * 1e-3)
+    # frames that arrive ENCODED: JPEG quality 90, 4:2:0, restart interval 2 MCUs, decoded on the device.
+    # (a) the packed scans of the batch sit in pinned host memory like the raw frames above; (b) a plain list of bytes objects
+    import cv2
+    js = [bytes(cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 2])[1]) for f in frames]
+    jb = sr.pack_jpeg_batch(js)
+    j_steps = e_steps if cfg_id != 4 else 20
+    for _ in sr.run_stream((jb for _ in range(sr.n_buf)), CONF, IOU, MIN_AREA, frame_ids=[ids_step] * sr.n_buf):
+        pass
+    h0 = sr.h2d_bytes
+    ms_j, n_rec_j = e2e_run((jb for _ in range(j_steps)), j_steps, [ids_step] * j_steps)
+    jpeg_h2d = (sr.h2d_bytes - h0) / j_steps
+    e2e_jpeg = world * B * j_steps / (ms_j * 1e-3)
+    ms_jl, _ = e2e_run((js for _ in range(p_steps)), p_steps, [ids_step] * p_steps)
+    e2e_jpeg_list = world * B * p_steps / (ms_jl * 1e-3)
+    dec_ = sr.jpeg[0]
+    hit_ = dec_.for_header(jb.hit[0])
+    import ctypes as _C
+    t_dec = timed(lambda: dec_.decode_device(hit_, sr.jdev[0], sr.joff[0], B, sr.dev[0], _C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    for b_ in range(sr.n_buf):
+        sr.host_buffer(b_, H, W)[:] = frames                # the ring holds raw frames again
     ceiling = h2d_ceiling(sr.host[0], sr.dev[0], sr.copy_stream)
     h2d_gbs = h2d_per_step / (ms_e / e_steps * 1e-3) / 1e9
 
@@ -657,6 +677,12 @@ def bench_pipeline(args):
                 "api": "B200Pipeline.stream().run_stream (pinned ring, copy stream, lanes, CUDA graph per step)",
                 "graph_steps": e2e_graph_steps, "direct_steps": e2e_direct_steps, "records": n_rec_e,
                 "h2d_gbs": h2d_gbs, "h2d_ceiling_gbs": ceiling, "frac_of_h2d_ceiling": h2d_gbs / ceiling if ceiling else None,
+                "jpeg_frames": {"value": e2e_jpeg, "steps": j_steps, "h2d_bytes_per_step": int(jpeg_h2d), "ms_per_step": ms_j / j_steps,
+                                "records": n_rec_j, "decode_ms_per_batch": t_dec,
+                                "value_from_bytes_objects": e2e_jpeg_list,
+                                "note": "same call with JPEG-encoded frames (quality 90, 4:2:0, restart interval 2 MCUs; "
+                                        f"{sum(len(j) for j in js) / len(js) / 1e3:.0f} kB/frame): scans packed in pinned host memory, decoded on the "
+                                        "device bit-exactly with cv2.imdecode; detections are those of the DECODED frames"},
                 "pageable_frames": {"value": e2e_pageable, "steps": p_steps,
                                     "note": "same call with ordinary (pageable) numpy frames: host copy into the pinned ring by "
                                             f"{sr.pool._max_workers} threads included"}},

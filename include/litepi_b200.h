@@ -230,8 +230,9 @@ typedef struct lp_jpeg_desc {
 } lp_jpeg_desc;
 size_t lp_jpeg_tables_bytes(void);
 size_t lp_jpeg_scratch_bytes(const lp_jpeg_desc* desc, int batch);
-int lp_jpeg_decode(lp_ctx* ctx, const uint8_t* data, const int64_t* img_off, int batch, const lp_jpeg_desc* desc,
-                   const void* tables, void* scratch, size_t scratch_bytes, uint8_t* frames_out, void* stream);
+int lp_jpeg_decode(lp_ctx* ctx, const uint8_t* data, const int64_t* img_off, int batch, int max_batch /* the scratch was sized for */,
+                   const lp_jpeg_desc* desc, const void* tables, void* scratch, size_t scratch_bytes, uint8_t* frames_out,
+                   void* stream);
 
 /* Workspace bytes lp_detect_forward / lp_classify need for the loaded plan (0 if not loaded). */
 size_t lp_workspace_bytes(lp_ctx* ctx, int net);

@@ -81,7 +81,7 @@ _PROTOS = {
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lp_jpeg_tables_bytes": (C.c_size_t, []),
     "lp_jpeg_scratch_bytes": (C.c_size_t, [C.POINTER(JpegDesc), C.c_int]),
-    "lp_jpeg_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(JpegDesc), C.c_void_p, C.c_void_p,
+    "lp_jpeg_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(JpegDesc), C.c_void_p, C.c_void_p,
                                  C.c_size_t, C.c_void_p, C.c_void_p]),
     "lp_launch_count": (C.c_int64, [C.c_void_p]),
     "lp_debug_tc_timing": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -9,9 +9,10 @@
 // Scope: SOF0, 8 bit, one interleaved scan, 3 components with luma 1x1 / 2x1 / 2x2 (4:4:4, 4:2:2, 4:2:0) or grey.
 // Parallelism comes from restart intervals: one thread decodes one restart segment (Huffman decoding is serial inside
 // a segment), so the encoder should emit RSTn markers every few MCUs; a file without them decodes on one thread.
-// Three kernels: (1) marker scan -> segment offsets, (2) Huffman + dequantise + IDCT -> component planes,
-// (3) up-sample + colour convert -> HWC BGR u8 frames.
+// Four kernels: (1) marker scan -> segment offsets, (2a) Huffman decode -> quantised coefficients (one thread per restart
+// interval), (2b) dequantise + IDCT -> component planes (one thread per 8x8 block), (3) up-sample + colour -> HWC BGR u8.
 #include "common.cuh"
+#include <stdlib.h>
 
 struct JpegTables {                 // device blob built by the host (jpeg.py pack_tables)
     int qt[4][64];                  // quantisation tables, NATURAL order
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(1024) jpeg_marker_scan_kernel(const uint8_t* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// (2) Huffman decode + dequantise + IDCT.  Thread = (image, restart segment).
+// (2) Huffman decode, then dequantise + IDCT.
 // ---------------------------------------------------------------------------------------------
 struct JpegGeom {
     int width, height, ncomp;
@@ -89,6 +90,8 @@ struct JpegGeom {
     int pw[3], ph[3];                   // padded plane size (whole MCUs)
     long long plane_off[3];             // byte offset of component c's planes inside the scratch (image 0)
     long long plane_img[3];             // bytes per image of that plane
+    long long blk_off[3];               // first 8x8-block index of component c (blocks: [component][image][block row][block column])
+    long long coef_off, mask_off;       // byte offsets of the coefficient buffer (int16 [blocks][64]) and the AC masks (u64 [blocks])
 };
 
 struct BitReader {
@@ -96,15 +99,28 @@ struct BitReader {
     const uint8_t* end;
     unsigned long long acc;
     int n;
+    // Refill to more than 32 bits.  Fast path: four bytes at once from a 4-byte aligned address when none of them is 0xFF
+    // (no stuffing, no marker); otherwise byte by byte with 0xFF00 un-stuffing.  A marker ends the segment: zeros are fed.
     __device__ __forceinline__ void fill() {
-        while (n <= 48) {
+        while (n <= 32) {
+            if ((((unsigned long long)p) & 3ull) == 0 && p + 4 <= end) {
+                const unsigned w = __ldg(reinterpret_cast<const unsigned*>(p));
+                // any byte == 0xFF  <=>  any byte of ~w == 0x00
+                const unsigned x = ~w;
+                if (((x - 0x01010101u) & ~x & 0x80808080u) == 0) {
+                    acc = (acc << 32) | __byte_perm(w, 0, 0x0123);      // big-endian bit order
+                    n += 32;
+                    p += 4;
+                    continue;
+                }
+            }
             unsigned b = 0;
             if (p < end) {
                 b = *p;
                 if (b == 0xFF) {
                     const unsigned nx = (p + 1 < end) ? p[1] : 0xD9u;
                     if (nx == 0) p += 2;
-                    else b = 0;                       // a marker ends the segment: feed zeros, stay
+                    else b = 0;
                 } else {
                     ++p;
                 }
@@ -138,45 +154,53 @@ __device__ __forceinline__ int huff_decode(BitReader& br, const JpegTables* __re
     return 0;                                           // corrupt stream: keep going, the frame will simply be wrong
 }
 
-// jidctint.c jpeg_idct_islow, one 8-point pass; SHIFT = CONST_BITS - PASS1_BITS (pass 1) or CONST_BITS + PASS1_BITS + 3 (pass 2)
+// jidctint.c jpeg_idct_islow, one 8-point pass on values in registers; SHIFT = CONST_BITS - PASS1_BITS (pass 1) or
+// CONST_BITS + PASS1_BITS + 3 (pass 2).  32-bit arithmetic: libjpeg's scaling is designed so that no intermediate exceeds
+// 32 bits for 8-bit samples (jidctint.c header comment), so this equals its JLONG arithmetic on every legal stream.
 template <int SHIFT>
-__device__ __forceinline__ void idct8(const int* x, int stride, int* o, int ostride) {
-    const long long c0541 = 4433, c0765 = 6270, c1847 = 15137, c1175 = 9633, c0298 = 2446, c2053 = 16819, c3072 = 25172,
-                    c1501 = 12299, c0899 = 7373, c2562 = 20995, c1961 = 16069, c0390 = 3196;
-    long long z2 = x[2 * stride], z3 = x[6 * stride];
-    long long z1 = (z2 + z3) * c0541;
-    const long long tmp2 = z1 - z3 * c1847, tmp3 = z1 + z2 * c0765;
-    const long long tmp0 = ((long long)x[0] + x[4 * stride]) << 13, tmp1 = ((long long)x[0] - x[4 * stride]) << 13;
-    const long long tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
-    long long t0 = x[7 * stride], t1 = x[5 * stride], t2 = x[3 * stride], t3 = x[1 * stride];
-    z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2;
-    long long z4 = t1 + t3;
-    const long long z5 = (z3 + z4) * c1175;
-    t0 *= c0298; t1 *= c2053; t2 *= c3072; t3 *= c1501;
-    z1 *= -c0899; z2 *= -c2562; z3 = z3 * -c1961 + z5; z4 = z4 * -c0390 + z5;
+__device__ __forceinline__ void idct8(int x0, int x1, int x2, int x3, int x4, int x5, int x6, int x7, int* o) {
+    int z1 = (x2 + x6) * 4433;
+    const int tmp2 = z1 - x6 * 15137, tmp3 = z1 + x2 * 6270;
+    const int tmp0 = (x0 + x4) << 13, tmp1 = (x0 - x4) << 13;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    int t0 = x7, t1 = x5, t2 = x3, t3 = x1;
+    z1 = t0 + t3;
+    int z2 = t1 + t2, z3 = t0 + t2, z4 = t1 + t3;
+    const int z5 = (z3 + z4) * 9633;
+    t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
+    z1 *= -7373; z2 *= -20995; z3 = z3 * -16069 + z5; z4 = z4 * -3196 + z5;
     t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
-    const long long r = 1ll << (SHIFT - 1);
-    o[0 * ostride] = (int)((tmp10 + t3 + r) >> SHIFT);
-    o[7 * ostride] = (int)((tmp10 - t3 + r) >> SHIFT);
-    o[1 * ostride] = (int)((tmp11 + t2 + r) >> SHIFT);
-    o[6 * ostride] = (int)((tmp11 - t2 + r) >> SHIFT);
-    o[2 * ostride] = (int)((tmp12 + t1 + r) >> SHIFT);
-    o[5 * ostride] = (int)((tmp12 - t1 + r) >> SHIFT);
-    o[3 * ostride] = (int)((tmp13 + t0 + r) >> SHIFT);
-    o[4 * ostride] = (int)((tmp13 - t0 + r) >> SHIFT);
+    constexpr int r = 1 << (SHIFT - 1);
+    o[0] = (tmp10 + t3 + r) >> SHIFT; o[7] = (tmp10 - t3 + r) >> SHIFT;
+    o[1] = (tmp11 + t2 + r) >> SHIFT; o[6] = (tmp11 - t2 + r) >> SHIFT;
+    o[2] = (tmp12 + t1 + r) >> SHIFT; o[5] = (tmp12 - t1 + r) >> SHIFT;
+    o[3] = (tmp13 + t0 + r) >> SHIFT; o[4] = (tmp13 - t0 + r) >> SHIFT;
 }
 
-__global__ void __launch_bounds__(128) jpeg_huffman_idct_kernel(const uint8_t* __restrict__ data, const long long* __restrict__ img_off,
-                                                                const int* __restrict__ seg_off, const int* __restrict__ seg_found,
-                                                                const JpegTables* __restrict__ T, JpegGeom g, int batch,
-                                                                uint8_t* __restrict__ planes) {
+constexpr int JH_THREADS = 128;
+
+// (2a) entropy decoding.  Thread = (image, restart segment).  The coefficients of the block being decoded live in shared
+// memory (column = thread: conflict-free 16-bit stores at data-dependent zigzag positions); a finished block goes to global
+// memory as eight 16-byte stores (natural order, zeros included), or as its DC value alone when it has no AC coefficient.
+// A 64-bit mask of the written AC positions tells the IDCT kernel which case it is.  The zigzag table is in shared memory
+// too: a constant-memory table indexed by a per-lane position serialises the warp.
+__global__ void __launch_bounds__(JH_THREADS, 6) jpeg_huffman_kernel(const uint8_t* __restrict__ data, const long long* __restrict__ img_off,
+                                                                      const int* __restrict__ seg_off, const int* __restrict__ seg_found,
+                                                                      const JpegTables* __restrict__ T, JpegGeom g, int batch,
+                                                                      short* __restrict__ coef, unsigned long long* __restrict__ mask) {
     __shared__ unsigned short s_lut[4][512];
-    for (int i = threadIdx.x; i < 4 * 512; i += blockDim.x) s_lut[i >> 9][i & 511] = T->lut[i >> 9][i & 511];
+    __shared__ unsigned char s_zz[64];
+    __shared__ __align__(16) short s_blk[64][JH_THREADS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * 512; i += blockDim.x) s_lut[i >> 9][i & 511] = T->lut[i >> 9][i & 511];
+    if (tid < 64) s_zz[tid] = c_zigzag[tid];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) s_blk[i][tid] = 0;
     __syncthreads();
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gid = (long long)blockIdx.x * blockDim.x + tid;
     if (gid >= (long long)batch * g.n_seg) return;
     const int img = (int)(gid / g.n_seg), seg = (int)(gid % g.n_seg);
-    if (seg >= seg_found[img]) return;                      // fewer markers than the header promises: leave the planes as they are
+    if (seg >= seg_found[img]) return;                      // fewer markers than the header promises: those blocks decode as zero
     const uint8_t* d0 = data + img_off[img];
     BitReader br;
     br.p = d0 + seg_off[(long long)img * g.n_seg + seg];
@@ -185,23 +209,19 @@ __global__ void __launch_bounds__(128) jpeg_huffman_idct_kernel(const uint8_t* _
     int pred[3] = {0, 0, 0};
     const int m0 = seg * (g.ri > 0 ? g.ri : g.n_mcu);
     const int m1 = min(g.n_mcu, m0 + (g.ri > 0 ? g.ri : g.n_mcu));
-    int blk[64], ws[64];
     for (int m = m0; m < m1; ++m) {
         const int my = m / g.mcux, mx = m - my * g.mcux;
         for (int ci = 0; ci < g.ncomp; ++ci) {
-            const int* __restrict__ q = T->qt[g.tq[ci]];
             const unsigned short* dlut = s_lut[g.td[ci]];
             const unsigned short* alut = s_lut[2 + g.ta[ci]];
+            const int bxn = g.mcux * g.h[ci], byn = g.mcuy * g.v[ci];
             for (int by = 0; by < g.v[ci]; ++by) {
                 for (int bx = 0; bx < g.h[ci]; ++bx) {
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) blk[i] = 0;
+                    const long long blk = g.blk_off[ci] + ((long long)img * byn + (my * g.v[ci] + by)) * bxn + (mx * g.h[ci] + bx);
                     br.fill();
                     int s = huff_decode(br, T, dlut, g.td[ci]);
-                    br.fill();
                     if (s) pred[ci] += jpeg_extend(br.get(s), s);
-                    blk[0] = pred[ci] * q[0];
-                    bool dc_only = true;
+                    unsigned long long used = 0ull;
                     for (int k = 1; k < 64;) {
                         br.fill();
                         const int rs = huff_decode(br, T, alut, 2 + g.ta[ci]);
@@ -214,34 +234,28 @@ __global__ void __launch_bounds__(128) jpeg_huffman_idct_kernel(const uint8_t* _
                         }
                         k += r;
                         const int v = jpeg_extend(br.get(s), s);
-                        if (k < 64) { const int nat = c_zigzag[k]; blk[nat] = v * q[nat]; dc_only = false; }
+                        if (k < 64) { const int nat = s_zz[k]; s_blk[nat][tid] = (short)v; used |= 1ull << nat; }
                         ++k;
                     }
-                    // ---- IDCT -> 8x8 samples of plane ci at block (my*v + by, mx*h + bx)
-                    uint8_t* dst = planes + g.plane_off[ci] + (long long)img * g.plane_img[ci] +
-                                   (long long)((my * g.v[ci] + by) * 8) * g.pw[ci] + (mx * g.h[ci] + bx) * 8;
-                    if (dc_only) {
-                        // both passes reduce to DESCALE((dc << PASS1_BITS) << CONST_BITS, CONST_BITS + PASS1_BITS + 3)
-                        const long long w0 = (long long)blk[0] << 2;
-                        int pv = (int)(((w0 << 13) + (1ll << 17)) >> 18) + 128;
-                        pv = min(max(pv, 0), 255);
-                        const unsigned w = (unsigned)pv * 0x01010101u;
-#pragma unroll
-                        for (int r8 = 0; r8 < 8; ++r8) *reinterpret_cast<uint2*>(dst + (long long)r8 * g.pw[ci]) = make_uint2(w, w);
+                    mask[blk] = used;
+                    short* __restrict__ cb = coef + blk * 64;
+                    if (used == 0ull) {
+                        cb[0] = (short)pred[ci];
                     } else {
+                        uint4* c4 = reinterpret_cast<uint4*>(cb);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) idct8<11>(blk + c, 8, ws + c, 8);          // pass 1: columns
+                        for (int q8 = 0; q8 < 8; ++q8) {
+                            unsigned w[4];
 #pragma unroll
-                        for (int r8 = 0; r8 < 8; ++r8) {
-                            int o[8];
-                            idct8<18>(ws + r8 * 8, 1, o, 1);                                    // pass 2: rows
-                            unsigned lo = 0, hi = 0;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                lo |= (unsigned)min(max(o[i] + 128, 0), 255) << (8 * i);
-                                hi |= (unsigned)min(max(o[4 + i] + 128, 0), 255) << (8 * i);
-                            }
-                            *reinterpret_cast<uint2*>(dst + (long long)r8 * g.pw[ci]) = make_uint2(lo, hi);
+                            for (int k2 = 0; k2 < 4; ++k2)
+                                w[k2] = (unsigned)(unsigned short)s_blk[q8 * 8 + 2 * k2][tid] | ((unsigned)(unsigned short)s_blk[q8 * 8 + 2 * k2 + 1][tid] << 16);
+                            if (q8 == 0) w[0] = (w[0] & 0xffff0000u) | (unsigned)(unsigned short)(short)pred[ci];
+                            c4[q8] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                        while (used) {                       // clear what this block wrote
+                            const int nat = __ffsll((long long)used) - 1;
+                            used &= used - 1;
+                            s_blk[nat][tid] = 0;
                         }
                     }
                 }
@@ -250,63 +264,183 @@ __global__ void __launch_bounds__(128) jpeg_huffman_idct_kernel(const uint8_t* _
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// (3) fancy up-sampling + YCbCr -> BGR.  Thread = 2 horizontally adjacent output pixels.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int chroma_at(const uint8_t* __restrict__ c, int pw, int hc, int wc, int oy, int ox, int hs, int vs) {
-    if (hs == 1 && vs == 1) return c[(long long)oy * pw + ox];
-    if (vs == 1) {                                          // h2v1
-        const int cx = ox >> 1;
-        const uint8_t* row = c + (long long)oy * pw;
-        const int v = row[cx];
-        if (ox & 1) return cx == wc - 1 ? v : (3 * v + row[cx + 1] + 2) >> 2;
-        return cx == 0 ? v : (3 * v + row[cx - 1] + 1) >> 2;
+// (2b) dequantise + IDCT.  Thread = one 8x8 block of one component; consecutive threads = consecutive blocks of a block row,
+// so the 8-byte row stores of a warp are contiguous.
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(const short* __restrict__ coef, const unsigned long long* __restrict__ mask,
+                                                        const JpegTables* __restrict__ T, JpegGeom g, int ci, int batch,
+                                                        uint8_t* __restrict__ planes) {
+    __shared__ short s_q[64];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_q[i] = (short)T->qt[g.tq[ci]][i];
+    __syncthreads();
+    const int bxn = g.mcux * g.h[ci], byn = g.mcuy * g.v[ci];
+    const int xb = blockIdx.x * blockDim.x + threadIdx.x;         // grid = (blocks along the block row, block row, image)
+    if (xb >= bxn) return;
+    const int yb = blockIdx.y, img = blockIdx.z;
+    const long long blk = g.blk_off[ci] + ((long long)img * byn + yb) * bxn + xb;
+    uint8_t* dst = planes + g.plane_off[ci] + (long long)img * g.plane_img[ci] + (long long)(yb * 8) * g.pw[ci] + xb * 8;
+    const unsigned long long used = mask[blk];
+    const short* cb = coef + blk * 64;
+    if (used == 0ull) {
+        // DC only: both passes reduce to DESCALE((dc << PASS1_BITS) << CONST_BITS, CONST_BITS + PASS1_BITS + 3)
+        const int dc = (int)cb[0] * (int)s_q[0];
+        int pv = (((dc << 2) << 13) + (1 << 17)) >> 18;
+        pv = min(max(pv + 128, 0), 255);
+        const unsigned w = (unsigned)pv * 0x01010101u;
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) *reinterpret_cast<uint2*>(dst + (long long)r8 * g.pw[ci]) = make_uint2(w, w);
+        return;
     }
-    const int cy = oy >> 1, cx = ox >> 1;                   // h2v2
+    int x[64];
+    const uint4* c4 = reinterpret_cast<const uint4*>(cb);
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+        const uint4 v = __ldg(c4 + q8);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            x[q8 * 8 + 2 * k] = (int)(short)(w[k] & 0xffffu) * (int)s_q[q8 * 8 + 2 * k];
+            x[q8 * 8 + 2 * k + 1] = (int)(short)(w[k] >> 16) * (int)s_q[q8 * 8 + 2 * k + 1];
+        }
+    }
+    int ws[64];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        int o[8];
+        idct8<11>(x[c], x[8 + c], x[16 + c], x[24 + c], x[32 + c], x[40 + c], x[48 + c], x[56 + c], o);       // pass 1: column c
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) ws[r8 * 8 + c] = o[r8];
+    }
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) {
+        int o[8];
+        idct8<18>(ws[r8 * 8], ws[r8 * 8 + 1], ws[r8 * 8 + 2], ws[r8 * 8 + 3], ws[r8 * 8 + 4], ws[r8 * 8 + 5], ws[r8 * 8 + 6], ws[r8 * 8 + 7], o);
+        unsigned lo = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            lo |= (unsigned)min(max(o[i] + 128, 0), 255) << (8 * i);
+            hi |= (unsigned)min(max(o[4 + i] + 128, 0), 255) << (8 * i);
+        }
+        *reinterpret_cast<uint2*>(dst + (long long)r8 * g.pw[ci]) = make_uint2(lo, hi);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (3) fancy up-sampling + YCbCr -> BGR.  Thread = 8 horizontally adjacent output pixels of one row.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ycc_px(int y, int cb, int cr) {       // returns B | G << 8 | R << 16
+    cb -= 128; cr -= 128;
+    // jdcolor.c: FIX(x) = (int)(x * 65536 + 0.5); arithmetic right shifts
+    const int rr = y + ((91881 * cr + 32768) >> 16);
+    const int gg = y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+    const int bb = y + ((116130 * cb + 32768) >> 16);
+    return (unsigned)min(max(bb, 0), 255) | ((unsigned)min(max(gg, 0), 255) << 8) | ((unsigned)min(max(rr, 0), 255) << 16);
+}
+
+// chroma samples of output columns [x0, x0 + 8) of output row oy into c8[8]
+__device__ __forceinline__ void chroma8(const uint8_t* __restrict__ c, int pw, int hc, int wc, int oy, int x0, int hs, int vs, int* c8) {
+    if (hs == 1) {
+        const uint8_t* row = c + (long long)oy * pw + x0;
+        const uint2 v = *reinterpret_cast<const uint2*>(row);        // planes are padded to whole MCUs: 8 bytes are always there
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { c8[k] = (v.x >> (8 * k)) & 255; c8[4 + k] = (v.y >> (8 * k)) & 255; }
+        return;
+    }
+    const int cx0 = x0 >> 1;                                       // 4 chroma columns cx0 .. cx0 + 3, plus one neighbour each side
+    int cs[6];
+    if (vs == 1) {                                                  // h2v1: rows are not mixed
+        const uint8_t* r0 = c + (long long)oy * pw;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cs[k] = r0[min(max(cx0 - 1 + k, 0), wc - 1)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cx = cx0 + k, v = cs[k + 1];
+            c8[2 * k] = cx == 0 ? v : (3 * v + cs[k] + 1) >> 2;
+            c8[2 * k + 1] = cx >= wc - 1 ? v : (3 * v + cs[k + 2] + 2) >> 2;
+        }
+        return;
+    }
+    const int cy = oy >> 1;
     const int cyn = (oy & 1) ? min(cy + 1, hc - 1) : max(cy - 1, 0);
     const uint8_t* r0 = c + (long long)cy * pw;
     const uint8_t* r1 = c + (long long)cyn * pw;
-    const int cs = 3 * r0[cx] + r1[cx];
-    if (ox & 1) {
-        if (cx == wc - 1) return (4 * cs + 7) >> 4;
-        return (3 * cs + 3 * r0[cx + 1] + r1[cx + 1] + 7) >> 4;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const int cx = min(max(cx0 - 1 + k, 0), wc - 1); cs[k] = 3 * r0[cx] + r1[cx]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int cx = cx0 + k, v = cs[k + 1];
+        c8[2 * k] = cx == 0 ? (4 * v + 8) >> 4 : (3 * v + cs[k] + 8) >> 4;
+        c8[2 * k + 1] = cx >= wc - 1 ? (4 * v + 7) >> 4 : (3 * v + cs[k + 2] + 7) >> 4;
     }
-    if (cx == 0) return (4 * cs + 8) >> 4;
-    return (3 * cs + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
 }
 
 __global__ void __launch_bounds__(256) jpeg_color_kernel(const uint8_t* __restrict__ planes, JpegGeom g, int batch, uint8_t* __restrict__ out) {
     const int W = g.width, H = g.height;
-    const int wp = (W + 1) >> 1;                            // pixel pairs per row
-    const long long total = (long long)batch * H * wp;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int px = (int)(i % wp) * 2;
-    long long r = i / wp;
-    const int oy = (int)(r % H), img = (int)(r / H);
-    const uint8_t* Y = planes + g.plane_off[0] + (long long)img * g.plane_img[0] + (long long)oy * g.pw[0];
-    uint8_t* o = out + (((long long)img * H + oy) * W + px) * 3;
-    const int npx = min(2, W - px);
+    const int wg = (W + 7) >> 3;                            // groups of 8 pixels per row
+    __shared__ __align__(16) uint8_t s_stage[256 * 24 + 32];
+    __shared__ long long s_base;
+    __shared__ int s_end;
+    // grid = (blocks along the row, row, image): a 64-bit division per thread cost more than the colour arithmetic
+    const int gi0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = gi0 < wg;
+    const int gi = valid ? gi0 : wg - 1;                     // out-of-range threads recompute the last group and store nothing
+    const int x0 = gi * 8;
+    const int oy = blockIdx.y, img = blockIdx.z;
+    const uint8_t* Y = planes + g.plane_off[0] + (long long)img * g.plane_img[0] + (long long)oy * g.pw[0] + x0;
+    const uint2 yv = *reinterpret_cast<const uint2*>(Y);   // pitch and x0 are multiples of 8
+    int y8[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { y8[k] = (yv.x >> (8 * k)) & 255; y8[4 + k] = (yv.y >> (8 * k)) & 255; }
+    unsigned p3[8];                                         // B | G << 8 | R << 16 per pixel
     if (g.ncomp == 1) {
-        for (int k = 0; k < npx; ++k) { const uint8_t v = Y[px + k]; o[3 * k] = v; o[3 * k + 1] = v; o[3 * k + 2] = v; }
-        return;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p3[k] = (unsigned)y8[k] * 0x010101u;
+    } else {
+        const int hs = g.hmax / g.h[1], vs = g.vmax / g.v[1];
+        const int wc = (W * g.h[1] + g.hmax - 1) / g.hmax, hc = (H * g.v[1] + g.vmax - 1) / g.vmax;     // real down-sampled size
+        int cb8[8], cr8[8];
+        chroma8(planes + g.plane_off[1] + (long long)img * g.plane_img[1], g.pw[1], hc, wc, oy, x0, hs, vs, cb8);
+        chroma8(planes + g.plane_off[2] + (long long)img * g.plane_img[2], g.pw[2], hc, wc, oy, x0, hs, vs, cr8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p3[k] = ycc_px(y8[k], cb8[k], cr8[k]);
     }
-    const int hs = g.hmax / g.h[1], vs = g.vmax / g.v[1];
-    const int wc = (W * g.h[1] + g.hmax - 1) / g.hmax, hc = (H * g.v[1] + g.vmax - 1) / g.vmax;     // real down-sampled size
-    const uint8_t* CB = planes + g.plane_off[1] + (long long)img * g.plane_img[1];
-    const uint8_t* CR = planes + g.plane_off[2] + (long long)img * g.plane_img[2];
-    for (int k = 0; k < npx; ++k) {
-        const int ox = px + k;
-        const int y = Y[ox];
-        const int cb = chroma_at(CB, g.pw[1], hc, wc, oy, ox, hs, vs) - 128;
-        const int cr = chroma_at(CR, g.pw[2], hc, wc, oy, ox, hs, vs) - 128;
-        // jdcolor.c: FIX(x) = (int)(x * 65536 + 0.5); arithmetic right shifts
-        const int rr = y + ((91881 * cr + 32768) >> 16);
-        const int gg = y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
-        const int bb = y + ((116130 * cb + 32768) >> 16);
-        o[3 * k + 0] = (uint8_t)min(max(bb, 0), 255);
-        o[3 * k + 1] = (uint8_t)min(max(gg, 0), 255);
-        o[3 * k + 2] = (uint8_t)min(max(rr, 0), 255);
+    // 8 pixels x 3 bytes = six 32-bit words: pixels 4j .. 4j+3 fill words 3j .. 3j+2
+    unsigned w[6];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        w[3 * j + 0] = p3[4 * j] | (p3[4 * j + 1] << 24);
+        w[3 * j + 1] = (p3[4 * j + 1] >> 8) | (p3[4 * j + 2] << 16);
+        w[3 * j + 2] = (p3[4 * j + 2] >> 16) | (p3[4 * j + 3] << 8);
+    }
+    // The frames are one contiguous [img][y][x][3] array and consecutive threads own consecutive pixel groups, so the block's
+    // output is one contiguous byte span.  Stage it in shared memory at an offset congruent to the global address modulo 16,
+    // then copy it out with aligned 16-byte stores (direct 4-byte stores at a 24-byte lane stride cost six partial-sector
+    // writes per sector).
+    const int npx = valid ? min(8, W - x0) : 0;
+    const long long goff = valid ? (((long long)img * H + oy) * W + x0) * 3 : 0;       // byte offset of this thread's pixels
+    if (threadIdx.x == 0) { s_base = goff; }
+    __syncthreads();
+    const long long base = s_base;
+    const int mis = (int)(((unsigned long long)(out + base)) & 15ull);
+    const int so = mis + (int)(goff - base);                  // byte offset inside the staging buffer
+    if (npx == 8 && (so & 3) == 0) {
+        unsigned* d32 = reinterpret_cast<unsigned*>(s_stage + so);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d32[k] = w[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < npx) { s_stage[so + 3 * k] = (uint8_t)(p3[k] & 255u); s_stage[so + 3 * k + 1] = (uint8_t)((p3[k] >> 8) & 255u); s_stage[so + 3 * k + 2] = (uint8_t)(p3[k] >> 16); }
+    }
+    if (valid && (threadIdx.x == blockDim.x - 1 || gi0 == wg - 1)) s_end = so + 3 * npx;
+    __syncthreads();
+    const int end = s_end;                                     // staged bytes are [mis, end)
+    uint8_t* gb = out + base - mis;                            // 16-byte aligned global address of staging offset 0
+    for (int c = threadIdx.x * 16; c < end; c += blockDim.x * 16) {
+        if (c >= mis && c + 16 <= end) {
+            *reinterpret_cast<uint4*>(gb + c) = *reinterpret_cast<const uint4*>(s_stage + c);
+        } else {
+            for (int k = max(c, mis); k < min(c + 16, end); ++k) gb[k] = s_stage[k];
+        }
     }
 }
 
@@ -335,6 +469,10 @@ static int jpeg_geom(const lp_jpeg_desc* d, JpegGeom& g, size_t* scratch_bytes, 
         g.plane_off[c] = (long long)off;
         off += ((size_t)batch * g.plane_img[c] + 255) / 256 * 256;
     }
+    long long nblk = 0;
+    for (int c = 0; c < g.ncomp; ++c) { g.blk_off[c] = nblk; nblk += (long long)batch * (g.mcux * g.h[c]) * (g.mcuy * g.v[c]); }
+    g.coef_off = (long long)off; off += ((size_t)nblk * 128 + 255) / 256 * 256;
+    g.mask_off = (long long)off; off += ((size_t)nblk * 8 + 255) / 256 * 256;
     *scratch_bytes = off;
     return 0;
 }
@@ -348,26 +486,44 @@ extern "C" size_t lp_jpeg_scratch_bytes(const lp_jpeg_desc* desc, int batch) {
 
 extern "C" size_t lp_jpeg_tables_bytes(void) { return sizeof(JpegTables); }
 
-extern "C" int lp_jpeg_decode(lp_ctx* ctx, const uint8_t* data, const int64_t* img_off, int batch, const lp_jpeg_desc* desc,
+extern "C" int lp_jpeg_decode(lp_ctx* ctx, const uint8_t* data, const int64_t* img_off, int batch, int max_batch, const lp_jpeg_desc* desc,
                               const void* tables, void* scratch, size_t scratch_bytes, uint8_t* frames_out, void* stream) {
     LP_CHECK(ctx && data && img_off && desc && tables && scratch && frames_out, "lp_jpeg_decode: null argument");
     lp_device_guard dev_guard(ctx);
     if (batch <= 0) return 0;
+    LP_CHECK(batch <= max_batch, "lp_jpeg_decode: batch %d > max_batch %d", batch, max_batch);
     JpegGeom g{};
     size_t need = 0;
-    if (jpeg_geom(desc, g, &need, batch)) return -1;
+    if (jpeg_geom(desc, g, &need, max_batch)) return -1;      // the scratch layout is that of max_batch whatever this call's batch
     LP_CHECK(scratch_bytes >= need, "lp_jpeg_decode: scratch %zu B < %zu B", scratch_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
     int* seg_off = (int*)scratch;
     int* seg_found = seg_off + (size_t)batch * g.n_seg;
+    static int stop = -1;                                  // debugging (tools/jpeg_time.py): LP_JPEG_STOP=1|2 ends after that kernel
+    if (stop < 0) { const char* e = getenv("LP_JPEG_STOP"); stop = e ? atoi(e) : 0; }
     jpeg_marker_scan_kernel<<<batch, 1024, 0, st>>>(data, (const long long*)img_off, g.n_seg, seg_off, seg_found);
     LP_LAUNCH_OK(ctx);
+    if (stop == 1) return 0;
     const long long threads = (long long)batch * g.n_seg;
-    jpeg_huffman_idct_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(data, (const long long*)img_off, seg_off, seg_found,
-                                                                                (const JpegTables*)tables, g, batch, (uint8_t*)scratch);
+    short* coef = (short*)((uint8_t*)scratch + g.coef_off);
+    unsigned long long* mask = (unsigned long long*)((uint8_t*)scratch + g.mask_off);
+    jpeg_huffman_kernel<<<(unsigned)((threads + JH_THREADS - 1) / JH_THREADS), JH_THREADS, 0, st>>>(data, (const long long*)img_off, seg_off, seg_found,
+                                                                                              (const JpegTables*)tables, g, batch, coef, mask);
     LP_LAUNCH_OK(ctx);
-    const long long pairs = (long long)batch * g.height * ((g.width + 1) / 2);
-    jpeg_color_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>((const uint8_t*)scratch, g, batch, frames_out);
+    if (stop == 3) return 0;
+    for (int c = 0; c < g.ncomp; ++c) {
+        const int bxn = g.mcux * g.h[c], byn = g.mcuy * g.v[c];
+        const int bt = bxn >= 128 ? 128 : (bxn + 31) / 32 * 32;
+        jpeg_idct_kernel<<<dim3((bxn + bt - 1) / bt, byn, batch), bt, 0, st>>>(coef, mask, (const JpegTables*)tables, g, c, batch, (uint8_t*)scratch);
+        LP_LAUNCH_OK(ctx);
+    }
+    if (stop == 2) return 0;
+    {
+        const int wg = (g.width + 7) / 8;
+        const int bt = wg >= 256 ? 256 : (wg + 31) / 32 * 32;
+        LP_CHECK(g.height <= 65535 && batch <= 65535, "lp_jpeg_decode: image too tall / batch too large for the colour grid");
+        jpeg_color_kernel<<<dim3((wg + bt - 1) / bt, g.height, batch), bt, 0, st>>>((const uint8_t*)scratch, g, batch, frames_out);
+    }
     LP_LAUNCH_OK(ctx);
     return 0;
 }

@@ -158,6 +158,11 @@ class JpegBatchDecoder:
         self._cache: Dict[bytes, Tuple[JpegHeader, L.JpegDesc, torch.Tensor, torch.Tensor]] = {}
 
     def header(self, buf) -> Tuple[JpegHeader, L.JpegDesc, torch.Tensor, torch.Tensor]:
+        last = getattr(self, "_last", None)                 # a stream repeats one header: compare bytes before parsing
+        if last is not None:
+            hb = last[0].header_bytes
+            if len(buf) >= len(hb) and bytes(buf[:len(hb)]) == hb:
+                return last
         hd = parse_header(buf)
         hit = self._cache.get(hd.header_bytes)
         if hit is None:
@@ -167,7 +172,13 @@ class JpegBatchDecoder:
                 scratch = torch.zeros(L.lib().lp_jpeg_scratch_bytes(C.byref(desc), self.max_batch), dtype=torch.uint8, device=self.device)
             hit = (hd, desc, tables, scratch)
             self._cache[hd.header_bytes] = hit
+        self._last = hit
         return hit
+
+    def for_header(self, hd: JpegHeader):
+        """tables + scratch of THIS decoder for an already parsed header (a lane picks up a batch packed by another)"""
+        hit = self._cache.get(hd.header_bytes)
+        return hit if hit is not None else self.header(hd.header_bytes + b"\xff\xd9")
 
     def stage(self, jpegs: Sequence, host_bytes: np.ndarray, host_off: np.ndarray):
         """Concatenate the entropy-coded scans of `jpegs` into `host_bytes` (pinned u8), offsets into `host_off` (int64 [B+1]).
@@ -194,7 +205,7 @@ class JpegBatchDecoder:
         if out_frames.shape[1] != hd.height or out_frames.shape[2] != hd.width:
             raise ValueError("output frame buffer does not match the JPEG size")
         L.check(L.lib().lp_jpeg_decode(self.ctx.handle, C.c_void_p(data_dev.data_ptr()), C.c_void_p(off_dev.data_ptr()), int(n),
-                                       C.byref(desc), C.c_void_p(tables.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                       self.max_batch, C.byref(desc), C.c_void_p(tables.data_ptr()), C.c_void_p(scratch.data_ptr()),
                                        scratch.numel(), C.c_void_p(out_frames.data_ptr()), stream), "lp_jpeg_decode")
 
     def decode(self, jpegs: Sequence) -> torch.Tensor:

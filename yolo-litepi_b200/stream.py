@@ -32,6 +32,17 @@ from .jpeg import JpegBatchDecoder, is_jpeg
 Frames = Union[np.ndarray, Sequence[np.ndarray]]
 
 
+class JpegBatch:
+    """A batch of same-header JPEGs already packed in PINNED host memory (``StreamRunner.pack_jpeg_batch``): the
+    compressed counterpart of a frame batch in the pinned ring -- the copy engine reads it directly."""
+
+    def __init__(self, hit, data: torch.Tensor, off: torch.Tensor, used: int, n: int):
+        self.hit, self.data, self.off, self.used, self.n = hit, data, off, int(used), int(n)
+
+    def __len__(self):
+        return self.n
+
+
 class StreamRunner:
     def __init__(self, pipe, lanes: int = 2, use_graph: Optional[bool] = None, copy_threads: Optional[int] = None):
         if lanes < 1:
@@ -91,6 +102,18 @@ class StreamRunner:
             self.joff = [torch.zeros((self.B + 1,), dtype=torch.int64, device=self.device) for _ in range(self.n_buf)]
         self.jcap = cap
 
+    def pack_jpeg_batch(self, jpegs: Sequence) -> JpegBatch:
+        """Concatenate the entropy-coded scans of same-header JPEG byte strings into one pinned buffer (+ offsets)."""
+        n = len(jpegs)
+        if n < 1 or n > self.B:
+            raise ValueError(f"a batch holds 1..{self.B} frames, got {n}")
+        total = sum(len(j) for j in jpegs)
+        data = torch.empty((max(total, 1),), dtype=torch.uint8).pin_memory()
+        off = torch.zeros((self.B + 1,), dtype=torch.int64).pin_memory()
+        hit, used = self.jpeg[0].stage(jpegs, data.numpy(), off.numpy())
+        off[n + 1:] = used
+        return JpegBatch(hit, data, off, used, n)
+
     def host_buffer(self, i: int, h: int, w: int) -> np.ndarray:
         """Pinned staging buffer ``i % n_buf`` as a [max_batch, h, w, 3] uint8 array.  Blocks until the copy engine has
         finished reading its previous contents, so a producer may overwrite it."""
@@ -108,6 +131,13 @@ class StreamRunner:
         n = len(frames)
         if n < 1 or n > self.B:
             raise ValueError(f"a batch holds 1..{self.B} frames, got {n}")
+        if isinstance(frames, JpegBatch):
+            hd = frames.hit[0]
+            self._ensure(hd.height, hd.width)
+            self._ensure_jpeg(frames.used)
+            # tables / scratch are per lane: look the header up in this lane's decoder
+            hit = self.jpeg[b % self.n_lanes].for_header(hd)
+            return n, ("jpegbatch", hit, frames)
         f0 = frames[0]
         if not isinstance(frames, (np.ndarray, torch.Tensor)) and is_jpeg(f0):
             # encoded frames: only the entropy-coded bytes cross PCIe, the decode runs on the lane's stream
@@ -191,11 +221,17 @@ class StreamRunner:
                     self.fid_h[b][:n] = torch.arange(n, dtype=torch.int32)
                 else:
                     self.fid_h[b][:n] = torch.as_tensor(frame_ids, dtype=torch.int32)
-                jpeg = isinstance(src, tuple) and src[0] == "jpeg"
+                jpeg = isinstance(src, tuple) and src[0] in ("jpeg", "jpegbatch")
                 with torch.cuda.stream(self.copy_stream):
                     if self.used[b]:
                         self.copy_stream.wait_event(self.consumed[b])
-                    if jpeg:
+                    if jpeg and src[0] == "jpegbatch":
+                        jb = src[2]
+                        used = max(jb.used, 1)
+                        self.jdev[b][:used].copy_(jb.data[:used], non_blocking=True)
+                        self.joff[b].copy_(jb.off, non_blocking=True)
+                        self.h2d_bytes += used + 8 * (self.B + 1)
+                    elif jpeg:
                         used = max(int(src[2]), 1)
                         self.jdev[b][:used].copy_(self.jhost[b][:used], non_blocking=True)
                         self.joff[b].copy_(self.joff_h[b], non_blocking=True)
