@@ -244,7 +244,7 @@ int lp_probe_read(lp_ctx* ctx, float* ms_h, int cap);
 
 /* Which kernel family ran each op of plan `net` in the last forward (host array, one int8 per op): 0 generic SIMT
  * kernel, 1 parameter-weight small-channel conv, 2 tcgen05 implicit-GEMM conv, 3 absorbed by the previous op's
- * kernel.  Returns the number of entries written.  With lp_probe_set(net, -2) every op gets one event pair
+ * kernel, 4 warp-level MMA small-channel conv.  Returns the number of entries written.  With lp_probe_set(net, -2) every op gets one event pair
  * (slot = op index; for the detector slot n_ops is the Detect tail). */
 int lp_op_paths(lp_ctx* ctx, int net, int8_t* out_h, int cap);
 

@@ -71,6 +71,7 @@ struct lp_ctx {
     lp_fused_cls* fused = nullptr;   // owned: fused-classifier program (lp_fused_classifier_load), freed by lp_destroy
     int attr_set = 0;                // bit per kernel family whose dynamic shared-memory opt-in was made on ctx->device
     int use_fused = 1;
+    int use_mma = 1;                 // warp-level MMA kernels for the small-channel layers (env LP_NO_MMA=1: fp32-FMA kernels instead)
     int use_pdl = 1;                 // programmatic dependent launch between tensor-core conv kernels (env LP_NO_PDL=1 disables)
     int roi_mode = 0;                // 0: e2e.py ROI rules + Pillow resize; 1: e2e_optimize.py rules + cv2 INTER_LINEAR
     const int* roi_count_dev = nullptr;   // lp_set_roi_count_device: ROI-side calls take their count from the device
@@ -110,6 +111,33 @@ __device__ __forceinline__ void split_make(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
 }
+
+// ---- layer-kernel parameter blocks (conv_simt.cu, conv_mma.cu) ----------------
+struct TensorRef {
+    const void* base;        // SPLIT16: hi plane; F32/U8: the data
+    long long plane;         // SPLIT16: element offset from hi to lo plane
+    long long img;           // elements per image (per plane)
+    int C;                   // total channels of the buffer
+    int coff;                // first channel of the view
+    int fmt;
+};
+
+struct ConvParams {
+    TensorRef in, out, res;  // res.base == nullptr -> no residual
+    int cin, cout, out_cstride;
+    int cout_real, seg_l0, seg_len, seg_pad;   // segmented destination (lp_op_desc.out_seg_len); seg_len == 0: plain
+    int H, W, Ho, Wo;        // input / output spatial size
+    int ksize, stride, act;
+    int res_first;           // LP_OPF_RES_BEFORE_ACT: act(conv + bias + residual)
+    int n_img;
+    const float* w;          // [tap][cin][cout]
+    const float* bias;       // [cout]
+    float in_scale_mean, in_scale_std;   // STEM_U8: x = (u8/255 - mean)/std ; detector: mean 0, std 1
+};
+
+// warp-level tensor-core path for the small-channel layers (conv_mma.cu): returns 1 if it ran the op (and, when *fused_next,
+// the 1x1 conv that follows it), 0 if the shape is not covered
+int lp_conv_mma_try(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st);
 
 // kernels implemented per translation unit (host launchers)
 int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, void* workspace,

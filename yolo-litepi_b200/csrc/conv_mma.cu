@@ -1,0 +1,293 @@
+// Small-channel convolutions on the warp-level tensor-core path (mma.sync m16n8k16, split-f16 operands).
+//
+// The first detector layers (model.ncnn.param:6-18: 3x3 s2 8->16, C2f cv1 1x1 16->16, bottleneck 3x3 8->8 twice, cv2 1x1
+// 24->16, all at 160x160) have GEMM shapes N = 8..16, K = 16..72.  A tcgen05 tile (M = 128, accumulators in TMEM, five warp
+// roles and six barrier hand-offs per tile) costs ~2500 fixed cycles per 128 pixels there -- slower than CUDA cores (r1
+// notes) -- and the fp32-FMA kernels that ran them instead are bound by instruction issue (ncu, profiles/r2_ncu_stage_kernels.txt:
+// 88-90 % issue-slot utilisation at 14-47 % of DRAM throughput).  A warp-level MMA needs no hand-off at all: a warp owns
+// 2 x 16 output pixels, takes its A fragments with ldmatrix straight from the shared-memory halo patch (one 16-byte row =
+// the 8 channels of one pixel of one tap, so im2col is only an address), keeps every weight fragment of the layer in
+// registers, and finishes bias / SiLU / residual / split in registers.  ~5x fewer instructions per pixel than the FMA
+// kernel; the layers move to their HBM bound.
+//
+// Numerics = the tcgen05 path's: value = hi + lo (fp16 each), product = Ahi*Bhi + Alo*Bhi + Ahi*Blo, fp32 accumulate.
+// Optional fused 1x1 (COUT -> COUT) on the activated result: the accumulator fragment of m16n8k16 IS the A fragment of the
+// next MMA (rows = pixels, k = channels), so the C2f cv1 behind the down-sampling conv never leaves the registers.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MM_THREADS = 128;            // 4 warps; block tile = 8 output rows x 16 output columns, 2 rows per warp
+constexpr int MM_TH = 8, MM_TW = 16;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;               // src-size 0: 16 bytes of zeros (halo / padding)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ float act1(float v, int act) {
+    if (act == LP_ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
+    if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == LP_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+    return v;
+}
+
+// (a, b) fp32 -> packed hi half2 and lo half2 (hi = rn(v), lo = rn(v - hi)): the split-f16 storage format
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// weight fragment of one k-step (two 8-channel slots) and one n-tile for this lane, split into hi / lo halves.
+// w = fp32 [tap][cin][cout] of the plan; slot s = tap * CH + chunk; B[k][n]: k 0-7 -> slot s0, 8-15 -> slot s1.
+__device__ __forceinline__ void load_bfrag(const float* __restrict__ w, int cin, int cout, int slot0, int slot1, int n_slots, int CH, int nt,
+                                           int lane, uint32_t (&bh)[2], uint32_t (&bl)[2]) {
+    const int n = nt * 8 + (lane >> 2), kc = (lane & 3) * 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int slot = h ? slot1 : slot0;
+        float x0 = 0.f, x1 = 0.f;
+        if (slot < n_slots && n < cout) {
+            const int tap = slot / CH, c = (slot - tap * CH) * 8 + kc;
+            x0 = __ldg(w + ((long long)tap * cin + c) * cout + n);
+            x1 = __ldg(w + ((long long)tap * cin + c + 1) * cout + n);
+        }
+        split2(x0, x1, bh[h], bl[h]);
+    }
+}
+
+// KS x KS conv, stride STRIDE, CH 8-channel chunks of input, NT 8-channel tiles of output; POST: fused 1x1 (8*NT -> 8*NT).
+template <int KS, int STRIDE, int CH, int NT, bool POST>
+__global__ void __launch_bounds__(MM_THREADS) conv_mma_kernel(const ConvParams p, const ConvParams q, int tiles_x, int tiles_y, int n_tiles) {
+    constexpr int PH = (MM_TH - 1) * STRIDE + KS, PW = (MM_TW - 1) * STRIDE + KS;
+    constexpr int SLOTS = KS * KS * CH, KSTEPS = (SLOTS + 1) / 2;
+    constexpr int PSTEPS = (NT + 1) / 2;                       // k-steps of the fused 1x1 (K = 8 * NT)
+    constexpr int PLANE = PH * PW * CH * 8;                    // halves per plane
+    __shared__ __align__(16) __half s_patch[2][2 * PLANE];      // two tiles: the next tile's patch loads while this one is in the MMAs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pad = KS / 2;
+
+    // ---- weight fragments of the whole layer, once per block
+    uint32_t bh[KSTEPS][NT][2], bl[KSTEPS][NT][2];
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) load_bfrag(p.w, p.cin, p.cout, 2 * s, 2 * s + 1, SLOTS, CH, nt, lane, bh[s][nt], bl[s][nt]);
+    uint32_t qh[POST ? PSTEPS : 1][NT][2], ql[POST ? PSTEPS : 1][NT][2];
+    if (POST) {
+#pragma unroll
+        for (int s = 0; s < PSTEPS; ++s)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) load_bfrag(q.w, q.cin, q.cout, 2 * s, 2 * s + 1, NT, NT, nt, lane, qh[s][nt], ql[s][nt]);
+    }
+    // ldmatrix row of this lane: matrix m = lane / 8 (m & 1: pixels 8-15, m >> 1: second slot of the k-step), row r = lane % 8
+    const int lm = lane >> 3, lr = lane & 7;
+    const int lj = lr + 8 * (lm & 1);                          // output column (inside the 16) this lane addresses
+    const int per_img = tiles_x * tiles_y;
+    // halo patch of `tile` -> shared memory buffer `buf`: [plane][py][px][chunk][8 halves]; one cp.async group per tile
+    auto load_patch = [&](int tile, int buf) {
+        const int img = tile / per_img, tr = tile - img * per_img;
+        const int oy0 = (tr / tiles_x) * MM_TH, ox0 = (tr % tiles_x) * MM_TW;
+        const __half* base = (const __half*)p.in.base + (long long)img * p.in.img + p.in.coff;
+        const int iy0 = oy0 * STRIDE - pad, ix0 = ox0 * STRIDE - pad;
+        const uint32_t pb = smem_addr(s_patch[buf]);
+        for (int e = tid; e < PH * PW * CH; e += MM_THREADS) {
+            const int ch = e % CH, pxl = e / CH;
+            const int py = pxl / PW, px = pxl - py * PW;
+            const int iy = iy0 + py, ix = ix0 + px;
+            const bool valid = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+            const __half* src = base + (valid ? (iy * p.W + ix) * p.in.C : 0) + ch * 8;
+            const uint32_t dst = pb + (uint32_t)e * 16;
+            cp16(dst, src, valid);
+            cp16(dst + PLANE * 2, src + p.in.plane, valid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int buf = 0;
+    if ((int)blockIdx.x < n_tiles) load_patch(blockIdx.x, 0);
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const int img = tile / per_img, tr = tile - img * per_img;
+        const int oy0 = (tr / tiles_x) * MM_TH, ox0 = (tr % tiles_x) * MM_TW;
+        const uint32_t patch0 = smem_addr(s_patch[buf]);
+        const bool more = tile + (int)gridDim.x < n_tiles;
+        if (more) load_patch(tile + gridDim.x, buf ^ 1);       // the other buffer was released by the barrier that ended the previous tile
+        // residual operands of this lane (C2f shortcut): issued now, consumed after the MMAs
+        uint32_t rres[2][2][NT][2];
+        const int cpair = (lane & 3) * 2;
+        if (!POST && p.res.base) {
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int oy = min(oy0 + 2 * warp + rt, p.Ho - 1), ox = min(ox0 + (lane >> 2) + 8 * hrow, p.Wo - 1);
+                    const __half* rh = (const __half*)p.res.base + (long long)img * p.res.img + (long long)(oy * p.Wo + ox) * p.res.C + p.res.coff;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        rres[rt][hrow][nt][0] = __ldg(reinterpret_cast<const unsigned*>(rh + nt * 8 + cpair));
+                        rres[rt][hrow][nt][1] = __ldg(reinterpret_cast<const unsigned*>(rh + p.res.plane + nt * 8 + cpair));
+                    }
+                }
+        }
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // ---- MMAs: this warp's two output rows
+        float acc[2][NT][4];
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[rt][nt][i] = 0.f;
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int oyl = 2 * warp + rt;
+            const uint32_t lane_base = patch0 + (uint32_t)(((oyl * STRIDE) * PW + lj * STRIDE) * CH) * 16;
+#pragma unroll
+            for (int s = 0; s < KSTEPS; ++s) {
+                const int s0 = 2 * s, s1 = (2 * s + 1 < SLOTS) ? 2 * s + 1 : 2 * s;      // a padded slot re-reads real data; its weights are zero
+                const int t0 = s0 / CH, c0 = s0 % CH, t1 = s1 / CH, c1 = s1 % CH;
+                const uint32_t off0 = (uint32_t)((((t0 / KS) * PW + (t0 % KS)) * CH + c0) * 16);
+                const uint32_t off1 = (uint32_t)((((t1 / KS) * PW + (t1 % KS)) * CH + c1) * 16);
+                const uint32_t addr = lane_base + ((lm >> 1) ? off1 : off0);
+                uint32_t ah[4], al[4];
+                ldsm4(addr, ah);
+                ldsm4(addr + PLANE * 2, al);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma16816(acc[rt][nt], ah, bh[s][nt][0], bh[s][nt][1]);
+                    mma16816(acc[rt][nt], al, bh[s][nt][0], bh[s][nt][1]);
+                    mma16816(acc[rt][nt], ah, bl[s][nt][0], bl[s][nt][1]);
+                }
+            }
+        }
+        __syncthreads();                                       // this buffer may be overwritten by the prefetch of the tile after next
+        // ---- epilogue.  Accumulator fragment: c0,c1 -> pixel lane/4, channels nt*8 + (lane%4)*2 + {0,1}; c2,c3 -> pixel lane/4 + 8
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int oy = oy0 + 2 * warp + rt;
+            float v[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float b0 = __ldg(p.bias + nt * 8 + cpair), b1 = __ldg(p.bias + nt * 8 + cpair + 1);
+                v[nt][0] = act1(acc[rt][nt][0] + b0, p.act); v[nt][1] = act1(acc[rt][nt][1] + b1, p.act);
+                v[nt][2] = act1(acc[rt][nt][2] + b0, p.act); v[nt][3] = act1(acc[rt][nt][3] + b1, p.act);
+            }
+            const ConvParams& o = POST ? q : p;
+            float w[NT][4];
+            if (POST) {
+                // activated result -> split -> A fragments of the 1x1: a0 = (row, k 0-7) = tile 2s c0,c1; a1 = rows + 8; a2, a3 = tile 2s + 1
+                float acc2[NT][4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc2[nt][i] = 0.f;
+#pragma unroll
+                for (int s = 0; s < PSTEPS; ++s) {
+                    uint32_t ah[4], al[4];
+                    split2(v[2 * s][0], v[2 * s][1], ah[0], al[0]);
+                    split2(v[2 * s][2], v[2 * s][3], ah[1], al[1]);
+                    if (2 * s + 1 < NT) {
+                        split2(v[2 * s + 1 < NT ? 2 * s + 1 : 0][0], v[2 * s + 1 < NT ? 2 * s + 1 : 0][1], ah[2], al[2]);
+                        split2(v[2 * s + 1 < NT ? 2 * s + 1 : 0][2], v[2 * s + 1 < NT ? 2 * s + 1 : 0][3], ah[3], al[3]);
+                    } else {
+                        ah[2] = ah[3] = al[2] = al[3] = 0u;
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        mma16816(acc2[nt], ah, qh[s][nt][0], qh[s][nt][1]);
+                        mma16816(acc2[nt], al, qh[s][nt][0], qh[s][nt][1]);
+                        mma16816(acc2[nt], ah, ql[s][nt][0], ql[s][nt][1]);
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const float b0 = __ldg(q.bias + nt * 8 + cpair), b1 = __ldg(q.bias + nt * 8 + cpair + 1);
+                    w[nt][0] = act1(acc2[nt][0] + b0, q.act); w[nt][1] = act1(acc2[nt][1] + b1, q.act);
+                    w[nt][2] = act1(acc2[nt][2] + b0, q.act); w[nt][3] = act1(acc2[nt][3] + b1, q.act);
+                }
+            } else {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[nt][i] = v[nt][i];
+            }
+            if (oy >= p.Ho) continue;
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int ox = ox0 + (lane >> 2) + 8 * hrow;
+                if (ox >= p.Wo) continue;
+                const int pix = oy * p.Wo + ox;
+                __half* oh = (__half*)o.out.base + (long long)img * o.out.img + (long long)pix * o.out.C + o.out.coff;
+                const bool has_res = !POST && p.res.base != nullptr;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    float x0 = w[nt][2 * hrow], x1 = w[nt][2 * hrow + 1];
+                    const int c = nt * 8 + cpair;
+                    if (has_res) {                              // C2f bottleneck shortcut: added after the activation
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rres[rt][hrow][nt][0]));
+                        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rres[rt][hrow][nt][1]));
+                        x0 += a.x + b.x; x1 += a.y + b.y;
+                    }
+                    uint32_t hi, lo;
+                    split2(x0, x1, hi, lo);
+                    *reinterpret_cast<uint32_t*>(oh + c) = hi;
+                    *reinterpret_cast<uint32_t*>(oh + o.out.plane + c) = lo;
+                }
+            }
+        }
+    }
+}
+
+template <int KS, int STRIDE, int CH, int NT, bool POST>
+int launch_mma(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st) {
+    const int tiles_x = (p.Wo + MM_TW - 1) / MM_TW, tiles_y = (p.Ho + MM_TH - 1) / MM_TH;
+    const long long n_tiles = (long long)tiles_x * tiles_y * p.n_img;
+    if (n_tiles <= 0 || n_tiles > 0x7fffffff) return 0;
+    // weights live in registers: a block amortises their load over several tiles; smem is small, so many blocks per SM hide latency
+    long long grid = (long long)ctx->sm_count * 8;
+    if (grid > n_tiles) grid = n_tiles;
+    const ConvParams q = post ? *post : p;
+    conv_mma_kernel<KS, STRIDE, CH, NT, POST><<<(unsigned)grid, MM_THREADS, 0, st>>>(p, q, tiles_x, tiles_y, (int)n_tiles);
+    return 1;
+}
+
+}  // namespace
+
+// Shapes covered: split-f16 in and out, channel views on 8-channel boundaries, cout == 8 * NT exactly.
+int lp_conv_mma_try(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st) {
+    if (p.in.fmt != LP_FMT_SPLIT16 || p.out.fmt != LP_FMT_SPLIT16 || p.in.coff % 8 || p.out.coff % 8 || p.cin % 8 || p.cout % 8) return 0;
+    if (p.seg_len != 0 || p.out_cstride != 1 || p.res_first) return 0;
+    if (p.res.base && (p.res.fmt != LP_FMT_SPLIT16 || p.res.coff % 8 || post)) return 0;
+    if (post && (post->cin != p.cout || post->cout != p.cout || post->out.fmt != LP_FMT_SPLIT16 || post->out.coff % 8 || post->res.base ||
+                 post->seg_len != 0 || post->out_cstride != 1))
+        return 0;
+    const int ch = p.cin / 8, nt = p.cout / 8;
+#define LP_MMA_CASE(K, S, C, N)                                                                   \
+    if (p.ksize == K && p.stride == S && ch == C && nt == N)                                       \
+        return post ? launch_mma<K, S, C, N, true>(ctx, p, post, st) : launch_mma<K, S, C, N, false>(ctx, p, nullptr, st);
+    LP_MMA_CASE(3, 2, 1, 2)      // v1 model.1   3x3 s2 8 -> 16 (+ model.2.cv1 1x1 16 -> 16)
+    LP_MMA_CASE(3, 1, 1, 1)      // v1 model.2.m 3x3 8 -> 8
+    LP_MMA_CASE(1, 1, 3, 2)      // v1 model.2.cv2 1x1 24 -> 16
+    LP_MMA_CASE(1, 1, 2, 2)      // v1 model.2.cv1 alone (per-op probing)
+    LP_MMA_CASE(1, 1, 5, 3)      // v2 model.2.cv2 1x1 36(40) -> 24
+    LP_MMA_CASE(1, 1, 3, 3)      // v2 model.2.cv1 alone
+#undef LP_MMA_CASE
+    return 0;
+}

@@ -7,28 +7,6 @@
 // Tensors are NHWC.  SPLIT16 buffers hold two fp16 planes (hi | lo), value = hi + lo.
 #include "common.cuh"
 
-struct TensorRef {
-    const void* base;        // SPLIT16: hi plane; F32/U8: the data
-    long long plane;         // SPLIT16: element offset from hi to lo plane
-    long long img;           // elements per image (per plane)
-    int C;                   // total channels of the buffer
-    int coff;                // first channel of the view
-    int fmt;
-};
-
-struct ConvParams {
-    TensorRef in, out, res;  // res.base == nullptr -> no residual
-    int cin, cout, out_cstride;
-    int cout_real, seg_l0, seg_len, seg_pad;   // segmented destination (lp_op_desc.out_seg_len); seg_len == 0: plain
-    int H, W, Ho, Wo;        // input / output spatial size
-    int ksize, stride, act;
-    int res_first;           // LP_OPF_RES_BEFORE_ACT: act(conv + bias + residual)
-    int n_img;
-    const float* w;          // [tap][cin][cout]
-    const float* bias;       // [cout]
-    float in_scale_mean, in_scale_std;   // STEM_U8: x = (u8/255 - mean)/std ; detector: mean 0, std 1
-};
-
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == LP_ACT_SILU) return v / (1.f + __expf(-v));
     if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
@@ -550,6 +528,36 @@ __global__ void dwconv3_kernel(ConvParams p) {
     st_elem(p.out, (long long)img * p.out.img + ((long long)oy * p.Wo + ox) * p.out.C + p.out.coff + out_chan(p, c), acc);
 }
 
+// 1x1 conv with a handful of outputs (the Detect head's class-logit convs: cout = nc, model.ncnn.param:160,171,182).  The
+// generic kernel stages a 32-wide weight slab and a patch per 8 input channels for one useful column; here a thread owns a
+// pixel, reads its cin channels with 16-byte loads and keeps the <= 4 accumulators in registers: the layer runs at the
+// speed of its input read.  Same fp32 operation order as the generic kernel (channels ascending, bias last).
+__global__ void __launch_bounds__(256) conv1x1_few_kernel(ConvParams p) {
+    extern __shared__ float s_wf[];                          // [cin][cout] then bias[cout]
+    for (int i = threadIdx.x; i < p.cin * p.cout; i += blockDim.x) s_wf[i] = __ldg(p.w + i);
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_wf[p.cin * p.cout + i] = __ldg(p.bias + i);
+    __syncthreads();
+    const long long total = (long long)p.n_img * p.Ho * p.Wo;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= total) return;
+    const int hw = p.Ho * p.Wo;
+    const int img = (int)(m / hw), q = (int)(m - (long long)img * hw);
+    const long long ipix = (long long)img * p.in.img + (long long)q * p.in.C + p.in.coff;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = 0; c0 < p.cin; c0 += 8) {
+        float v[8];
+        ld8(p.in, ipix + c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < p.cout) acc[j] = fmaf(v[i], s_wf[(c0 + i) * p.cout + j], acc[j]);
+    }
+    const long long opix = (long long)img * p.out.img + (long long)q * p.out.C + p.out.coff;
+    for (int j = 0; j < p.cout; ++j)
+        if (j < p.cout_real) st_elem(p.out, opix + out_chan(p, j), act_apply(acc[j] + s_wf[p.cin * p.cout + j], p.act));
+}
+
 // SqueezeExcitation pieces (torchvision ops/misc.py): mean over H x W per channel, and x * gate[c]
 __global__ void global_mean_kernel(ConvParams p) {
     const long long total = (long long)p.n_img * p.cout;
@@ -841,25 +849,52 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                 LP_CHECK(ob.h == p.Ho && ob.w == p.Wo, "op %zu: output buffer %dx%d != computed %dx%d", oi, ob.h, ob.w, p.Ho, p.Wo);
         }
         const long long total = (long long)batch * p.Ho * p.Wo * p.cout;
+        // A 1x1 conv of the same width that is the ONLY consumer of this conv's output (the C2f cv1 behind a down-sampling
+        // conv) can be applied in registers by the producing kernel: its input tensor is then never written or read.
+        auto post_candidate = [&]() -> int {
+            if (!(op.kind == LP_OP_CONV && op.ksize == 3 && op.res_buf < 0 && oi + 1 < net.ops.size())) return -1;
+            if (ctx->probe_net == net_id && (ctx->probe_op == -2 || ctx->probe_op == (int)oi || ctx->probe_op == (int)oi + 1)) return -1;
+            const lp_op_desc& o2 = net.ops[oi + 1];
+            bool ok2 = o2.kind == LP_OP_CONV && o2.ksize == 1 && o2.stride == 1 && o2.cin == op.cout && o2.cout == op.cout && o2.flags == 0 &&
+                       o2.in_buf == op.out_buf && o2.in_coff == op.out_coff && o2.res_buf < 0 && o2.out_seg_len == 0 &&
+                       o2.out_cstride <= 1 && o2.out_coff % 8 == 0 && net.bufs[o2.out_buf].fmt == LP_FMT_SPLIT16 &&
+                       net.bufs[o2.out_buf].h == ob.h && net.bufs[o2.out_buf].w == ob.w;
+            for (size_t k = 0; ok2 && k < net.ops.size(); ++k)
+                if (k != oi && k != oi + 1 && (net.ops[k].in_buf == op.out_buf || net.ops[k].res_buf == op.out_buf || net.ops[k].out_buf == op.out_buf))
+                    ok2 = false;
+            return ok2 ? (int)oi + 1 : -1;
+        };
+        // warp-level tensor-core path for the small-channel layers (conv_mma.cu)
+        if (ctx->use_tc && ctx->use_mma && op.kind == LP_OP_CONV && op.flags == 0 && op.out_seg_len == 0 && p.out_cstride == 1 &&
+            p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16 && op.cin <= 40 && op.cout <= 24 && (size_t)op.cout * 8 == (size_t)(op.cout / 8) * 64) {
+            const int post_idx = post_candidate();
+            ConvParams pq{};
+            if (post_idx >= 0) {
+                const lp_op_desc& o2 = net.ops[post_idx];
+                pq.cin = o2.cin; pq.cout = o2.cout; pq.act = o2.act; pq.out_cstride = 1; pq.cout_real = o2.cout;
+                pq.w = net.weights + o2.w_off; pq.bias = net.weights + o2.b_off;
+                pq.out = make_ref(net, o2.out_buf, o2.out_coff, ws, o2.row_off);
+                pq.Ho = p.Ho; pq.Wo = p.Wo; pq.n_img = batch; pq.ksize = 1; pq.stride = 1;
+            }
+            int r = lp_conv_mma_try(ctx, p, post_idx >= 0 ? &pq : nullptr, st);
+            if (r == 0 && post_idx >= 0) r = lp_conv_mma_try(ctx, p, nullptr, st) ? 2 : 0;      // shape covered, fusion not
+            if (r) {
+                LP_LAUNCH_OK(ctx);
+                net.last_path[oi] = 4;
+                if (r == 1 && post_idx >= 0) { ++oi; net.last_path[oi] = 3; }
+                continue;
+            }
+        }
         if ((op.kind == LP_OP_STEM_U8 || op.kind == LP_OP_CONV) && net.small_slot.size() > oi && net.small_slot[oi] >= 0 && op.flags == 0 &&
             (p.res.base == nullptr || (p.res.fmt == LP_FMT_SPLIT16 && p.res.coff % 8 == 0)) && p.seg_len == 0 &&
             p.out_cstride == 1 && p.out.fmt == LP_FMT_SPLIT16 &&
             (op.kind == LP_OP_STEM_U8 || p.in.fmt == LP_FMT_SPLIT16) && p.in.coff % 8 == 0 && p.out.coff % 8 == 0) {
-            // A 1x1 conv of the same width that is the ONLY consumer of this conv's output (the C2f cv1 behind a
-            // down-sampling conv) is applied in registers: its input tensor is never written or read.
-            int post_slot = -1, post_act = 0;
-            if (op.kind == LP_OP_CONV && op.ksize == 3 && op.res_buf < 0 && oi + 1 < net.ops.size() && net.small_slot[oi + 1] >= 0 &&
-                !(ctx->probe_net == net_id && (ctx->probe_op == -2 || ctx->probe_op == (int)oi || ctx->probe_op == (int)oi + 1))) {
-                const lp_op_desc& o2 = net.ops[oi + 1];
-                bool ok2 = o2.kind == LP_OP_CONV && o2.ksize == 1 && o2.stride == 1 && o2.cin == op.cout && o2.cout == op.cout &&
-                           o2.in_buf == op.out_buf && o2.in_coff == op.out_coff && o2.res_buf < 0 && o2.out_seg_len == 0 &&
-                           o2.out_cstride <= 1 && o2.out_coff % 8 == 0 && net.bufs[o2.out_buf].fmt == LP_FMT_SPLIT16 &&
-                           net.bufs[o2.out_buf].h == ob.h && net.bufs[o2.out_buf].w == ob.w;
-                for (size_t k = 0; ok2 && k < net.ops.size(); ++k)
-                    if (k != oi && k != oi + 1 && (net.ops[k].in_buf == op.out_buf || net.ops[k].res_buf == op.out_buf || net.ops[k].out_buf == op.out_buf))
-                        ok2 = false;
-                if (ok2) {
-                    post_slot = (int)oi + 1;
+                    int post_slot = -1, post_act = 0;
+            {
+                const int cand = post_candidate();
+                if (cand >= 0 && net.small_slot[cand] >= 0) {
+                    const lp_op_desc& o2 = net.ops[cand];
+                    post_slot = cand;
                     post_act = o2.act;
                     p.out = make_ref(net, o2.out_buf, o2.out_coff, ws, o2.row_off);
                 }
@@ -895,7 +930,11 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                 if (r < 0) return r;
                 if (r == 1) { ctx->launches++; net.last_path[oi] = 2; continue; }
             }
-            if (op.ksize == 1 && op.stride == 1) launch_conv<1, 1>(p, st);
+            if (op.ksize == 1 && op.stride == 1 && op.cout <= 4 && op.cin % 8 == 0 && p.in.fmt == LP_FMT_SPLIT16 && p.in.coff % 8 == 0 &&
+                p.res.base == nullptr && (size_t)(op.cin + 1) * op.cout * 4 <= 40 * 1024) {
+                const long long px = (long long)batch * p.Ho * p.Wo;
+                conv1x1_few_kernel<<<(unsigned)((px + 255) / 256), 256, (size_t)(op.cin + 1) * op.cout * sizeof(float), st>>>(p);
+            } else if (op.ksize == 1 && op.stride == 1) launch_conv<1, 1>(p, st);
             else if (op.ksize == 1 && op.stride == 2) launch_conv<1, 2>(p, st);
             else if (op.ksize == 3 && op.stride == 1) launch_conv<3, 1>(p, st);
             else if (op.ksize == 3 && op.stride == 2) launch_conv<3, 2>(p, st);
