@@ -344,7 +344,7 @@ def main():
     ap.add_argument("--detector", default="v1", choices=["v1", "v2"],
                     help="v1 = the reference's trained VN-Signs export; v2 = the paper's YOLO-LitePi widths (TT100K export, random-init: weights are not in the reference repo)")
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--lanes", type=int, default=2, help="batches in flight per GPU (pipeline instances on their own CUDA streams)")
+    ap.add_argument("--lanes", type=int, default=3, help="batches in flight per GPU (pipeline instances on their own CUDA streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="direct launches instead of the captured CUDA graph")
     ap.add_argument("--profile-mode", action="store_true",
