@@ -391,6 +391,10 @@ def bench_pipeline(args):
     B = args.batch or cfg["batch"]
     NC = cfg["classes"]
     param, binp = model_paths("vntsr" if args.detector == "v1" else "tt100k")
+    # random-init weights (the v2 / paper-width export ships without weights) score every anchor around 0.5: at conf 0.25 that
+    # is thousands of meaningless "detections" per frame.  The v2 line measures the ARCHITECTURE's throughput: a threshold no
+    # random score passes, so the ROI stages see an empty list (said in config_detail).
+    conf_t = CONF if binp else 0.999
     n_lanes = max(1, args.lanes)
     pipe = litepi_b200.B200Pipeline(param, binp, None, "shufflenetv2", num_classes=NC, device=local_rank, max_batch=B, seed=0)
     sr = pipe.stream(lanes=n_lanes, use_graph=False if (args.no_graph or args.profile_mode) else None)
@@ -437,11 +441,11 @@ def bench_pipeline(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     n_warm = max(args.warmup, sr.n_buf)                     # every ring buffer has its own graph
-    for _ in sr.run_stream(ring_batches(n_warm), CONF, IOU, MIN_AREA, frame_ids=[ids_step] * n_warm):
+    for _ in sr.run_stream(ring_batches(n_warm), conf_t, IOU, MIN_AREA, frame_ids=[ids_step] * n_warm):
         pass
     barrier()
     sampler.wait_first()
-    sr.replay_resident(n_lanes, CONF, IOU, MIN_AREA); sr.drain_resident(n_lanes)   # the wait above left the GPU idle: ramp the clocks again
+    sr.replay_resident(n_lanes, conf_t, IOU, MIN_AREA); sr.drain_resident(n_lanes)   # the wait above left the GPU idle: ramp the clocks again
     barrier()
 
     # ---------------- device-resident throughput (value): K steps replayed on the frames resident in the device ring
@@ -459,12 +463,12 @@ def bench_pipeline(args):
     for st_ in sr.lane_streams + [sr.copy_stream]:
         st_.wait_event(e0)
     if cfg_id == 4:
-        recs4 = list(sr.run_stream((dev_all[i * B:(i + 1) * B] for i in range(steps)), CONF, IOU, MIN_AREA,
+        recs4 = list(sr.run_stream((dev_all[i * B:(i + 1) * B] for i in range(steps)), conf_t, IOU, MIN_AREA,
                                    frame_ids=[ids_all[i * B:(i + 1) * B] for i in range(steps)]))
         local_rec = torch.from_numpy(np.concatenate(recs4)).to(dev) if recs4 else torch.zeros((0, 9), dtype=torch.int32, device=dev)
         gathered = gather_records(local_rec)                # inside the timed region: config 4 is the whole job
     else:
-        sr.replay_resident(steps, CONF, IOU, MIN_AREA)
+        sr.replay_resident(steps, conf_t, IOU, MIN_AREA)
         last = sr.drain_resident(steps)
     for st_ in sr.lane_streams:
         main_st.wait_stream(st_)
@@ -510,12 +514,12 @@ def bench_pipeline(args):
     n_probe = min(args.steps, 50)
     pipe.ctx.probe_set(L.NET_DETECTOR, dom)
     for _ in range(n_probe):
-        pipe.enqueue_device(fb0, CONF, IOU, MIN_AREA, fid0)
+        pipe.enqueue_device(fb0, conf_t, IOU, MIN_AREA, fid0)
     pipe.finish(fb0, fid0)
     probe = pipe.ctx.probe_read()
     pipe.ctx.probe_set(L.NET_DETECTOR, -2)
-    pipe.enqueue_device(fb0, CONF, IOU, MIN_AREA, fid0); pipe.finish(fb0, fid0)     # warm (unfused variants)
-    pipe.enqueue_device(fb0, CONF, IOU, MIN_AREA, fid0); pipe.finish(fb0, fid0)
+    pipe.enqueue_device(fb0, conf_t, IOU, MIN_AREA, fid0); pipe.finish(fb0, fid0)     # warm (unfused variants)
+    pipe.enqueue_device(fb0, conf_t, IOU, MIN_AREA, fid0); pipe.finish(fb0, fid0)
     per_op = pipe.ctx.probe_read()
     paths = pipe.ctx.op_paths(L.NET_DETECTOR)
     pipe.ctx.probe_set(L.NET_DETECTOR, -1)
@@ -540,10 +544,10 @@ def bench_pipeline(args):
     lb_ = det_.letterbox_device(fb0)
     t_fw = timed(lambda: det_.forward_device(lb_))
     out0_ = det_.forward_device(lb_)
-    t_nms = timed(lambda: det_.decode_nms_device(out0_, fb0.h[:B], fb0.w[:B], det_.ratio[:B], det_.pad[:2 * B], CONF, IOU))
+    t_nms = timed(lambda: det_.decode_nms_device(out0_, fb0.h[:B], fb0.w[:B], det_.ratio[:B], det_.pad[:2 * B], conf_t, IOU))
     n_cand = int(det_.n_cand[:B].sum())
     n_keep = int(torch.clamp(det_.counts[:B], max=det_.max_det).sum())
-    n_r = pipe.run_device(fb0, CONF, IOU, MIN_AREA, fid0)
+    n_r = pipe.run_device(fb0, conf_t, IOU, MIN_AREA, fid0)
     t_rs = timed(lambda: clf_.resize_device(fb0, pipe.roi_xyxy, pipe.roi_src, n_r)) if n_r else 0.0
     cls_in_ = clf_.resize_device(fb0, pipe.roi_xyxy, pipe.roi_src, n_r) if n_r else None
     t_cl = timed(lambda: clf_.classify_device(cls_in_)) if n_r else 0.0
@@ -569,7 +573,7 @@ def bench_pipeline(args):
         for st_ in sr.lane_streams + [sr.copy_stream]:
             st_.wait_event(e0)
         n_rec = 0
-        for rec in sr.run_stream(batches, CONF, IOU, MIN_AREA, frame_ids=fids):
+        for rec in sr.run_stream(batches, conf_t, IOU, MIN_AREA, frame_ids=fids):
             n_rec += rec.shape[0]
         for st_ in sr.lane_streams:
             main_st.wait_stream(st_)
@@ -585,7 +589,7 @@ def bench_pipeline(args):
         e2e_value = 4096 / (ms_e * 1e-3)
     else:
         e_steps = args.steps
-        for _ in sr.run_stream(ring_batches(sr.n_buf), CONF, IOU, MIN_AREA, frame_ids=[ids_step] * sr.n_buf):
+        for _ in sr.run_stream(ring_batches(sr.n_buf), conf_t, IOU, MIN_AREA, frame_ids=[ids_step] * sr.n_buf):
             pass
         ms_e, n_rec_e = e2e_run(ring_batches(e_steps), e_steps, [ids_step] * e_steps)
         e2e_value = world * B * e_steps / (ms_e * 1e-3)
@@ -603,7 +607,7 @@ def bench_pipeline(args):
     js = [bytes(cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 2])[1]) for f in frames]
     jb = sr.pack_jpeg_batch(js)
     j_steps = e_steps if cfg_id != 4 else 20
-    for _ in sr.run_stream((jb for _ in range(sr.n_buf)), CONF, IOU, MIN_AREA, frame_ids=[ids_step] * sr.n_buf):
+    for _ in sr.run_stream((jb for _ in range(sr.n_buf)), conf_t, IOU, MIN_AREA, frame_ids=[ids_step] * sr.n_buf):
         pass
     h0 = sr.h2d_bytes
     ms_j, n_rec_j = e2e_run((jb for _ in range(j_steps)), j_steps, [ids_step] * j_steps)
@@ -628,11 +632,11 @@ def bench_pipeline(args):
     for i in range(40):
         f1 = [frames[i % B]]
         t0 = time.perf_counter()
-        sr1.run_one(f1, CONF, IOU, MIN_AREA)
+        sr1.run_one(f1, conf_t, IOU, MIN_AREA)
         lat.append((time.perf_counter() - t0) * 1e3)
     for i in range(15):
         t0 = time.perf_counter()
-        pipe1.run(frames[i % B], CONF, IOU, MIN_AREA)           # the reference-shaped call (e2e.py:443), per-stage events + dict building
+        pipe1.run(frames[i % B], conf_t, IOU, MIN_AREA)           # the reference-shaped call (e2e.py:443), per-stage events + dict building
         lat_run.append((time.perf_counter() - t0) * 1e3)
     p50, p50_run = statistics.median(lat[8:]), statistics.median(lat_run[5:])
 
@@ -658,6 +662,7 @@ def bench_pipeline(args):
         "batch_per_gpu": B, "detector": args.detector,
         "weights": ("reference trained v1 (model.ncnn.bin)" if binp else "random-init seed 0 (weights not in the reference repo / not staged)"),
         "classifier_weights": "random-init seed 0 (reference ships none)",
+        "conf_used": conf_t,
         "workspace_gb": ws_gb,
         "rois_per_step": rois_per_step,
         "parallelism": f"frames sharded over {world} GPU(s); {n_lanes} batches in flight per GPU (CUDA streams), step = one CUDA graph",
