@@ -341,6 +341,36 @@ def test_detector_tensor_core_and_simt_paths(lp, v1_paths, tc):
     assert d[:, :4].max() < BOX_TOL and d[:, 4].max() < SCORE_TOL
 
 
+@pytest.mark.parametrize("which,size", [("v1", 640), ("v1", 416), ("v2", 640)])
+def test_fused_c2f_body_equals_layer_by_layer(lp, v1_paths, v2_paths, monkeypatch, tmp_path, which, size):
+    """csrc/c2f_mma.cu runs the bottleneck chain + cv2 of the c = 8 / 16 C2f blocks in one kernel.  Same arithmetic as the
+    layer-by-layer kernels (split-f16 three-product MMAs, fp32 accumulate, re-split between layers): out0 differs only by
+    fp32 summation order.  416 = 52 x 52 / 104 x 104 maps: tiles overhang the image on both axes."""
+    from litepi_b200 import _lib as L
+    param, binp = (v1_paths if which == "v1" else (v2_paths[0], None))
+    if size != 640:
+        from helpers import make_variant_param
+        param = make_variant_param(param, str(tmp_path / f"c2f_{size}.param"), nc=1, in_size=size)
+    x = np.random.default_rng(21).integers(0, 256, (3, size, size, 3), dtype=np.uint8)
+    det = lp.B200Detector(param, binp if size == 640 else None, input_size=size, max_batch=3, seed=3)
+    fused = det.forward(x)
+    paths = det.ctx.op_paths(L.NET_DETECTOR)
+    n_fused = sum(1 for v in paths if v == 5)
+    assert n_fused >= (3 if which == "v1" else 1), paths
+    monkeypatch.setenv("LP_NO_C2F", "1")
+    det2 = lp.B200Detector(param, binp if size == 640 else None, input_size=size, max_batch=3, seed=3)
+    monkeypatch.delenv("LP_NO_C2F")
+    layered = det2.forward(x)
+    assert 5 not in det2.ctx.op_paths(L.NET_DETECTOR)
+    d = np.abs(fused - layered)
+    assert d[:, :4].max() < 2e-3 and d[:, 4:].max() < 1e-4, (d[:, :4].max(), d[:, 4:].max())
+    orc = DetectorOracle(param, binp if size == 640 else None, seed=3, in_size=size)
+    _sync(orc, det.model)
+    ref = orc.forward(torch.from_numpy(x.astype(np.float32) / 255).permute(0, 3, 1, 2).contiguous()).numpy()
+    d = np.abs(fused - ref)
+    assert d[:, :4].max() < BOX_TOL and d[:, 4:].max() < SCORE_TOL
+
+
 def test_classifier_default_init_state_dict(lp):
     """the reference's own construction: torchvision random init + fc swap, default BatchNorm"""
     import torch.nn as nn

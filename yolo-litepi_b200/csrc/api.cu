@@ -36,6 +36,7 @@ extern "C" int lp_create(lp_ctx** out, int device) {
     c->device = device;
     { const char* e = getenv("LP_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
     { const char* e = getenv("LP_NO_MMA"); c->use_mma = (e && e[0] == '1') ? 0 : 1; }
+    { const char* e = getenv("LP_NO_C2F"); c->use_c2f = (e && e[0] == '1') ? 0 : 1; }
     c->sm_count = prop.multiProcessorCount;
     *out = c;
     return 0;

@@ -52,7 +52,7 @@ struct lp_net_plan {
     std::vector<int> small_slot;    // per op: >= 0 if the small-channel conv path (weights as kernel parameters) covers it
     std::vector<std::vector<float>> small_host;   // per op: host copy [weights | bias] for those ops
     std::vector<int8_t> last_path;  // per op, which kernel family ran it last (lp_op_paths): 0 generic SIMT, 1 parameter-weight
-                                    // small conv, 2 tcgen05 conv, 3 absorbed by the previous op's kernel
+                                    // small conv, 2 tcgen05 conv, 3 absorbed by the previous op's kernel, 4 warp-level MMA conv, 5 fused C2f body
 };
 
 struct lp_fused_cls;                // fused ShuffleNetV2 program of a context (shufflenet_fused.cu)
@@ -72,6 +72,7 @@ struct lp_ctx {
     int attr_set = 0;                // bit per kernel family whose dynamic shared-memory opt-in was made on ctx->device
     int use_fused = 1;
     int use_mma = 1;                 // warp-level MMA kernels for the small-channel layers (env LP_NO_MMA=1: fp32-FMA kernels instead)
+    int use_c2f = 1;                 // fused C2f-body kernel for c = 8 / 16 (env LP_NO_C2F=1: layer by layer)
     int use_pdl = 1;                 // programmatic dependent launch between tensor-core conv kernels (env LP_NO_PDL=1 disables)
     int roi_mode = 0;                // 0: e2e.py ROI rules + Pillow resize; 1: e2e_optimize.py rules + cv2 INTER_LINEAR
     const int* roi_count_dev = nullptr;   // lp_set_roi_count_device: ROI-side calls take their count from the device
@@ -138,6 +139,9 @@ struct ConvParams {
 // warp-level tensor-core path for the small-channel layers (conv_mma.cu): returns 1 if it ran the op (and, when *fused_next,
 // the 1x1 conv that follows it), 0 if the shape is not covered
 int lp_conv_mma_try(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st);
+
+// fused C2f body (c2f_mma.cu): number of plan ops covered starting at op `oi` (0: pattern / shape not covered, < 0: error)
+int lp_c2f_fused_try(lp_ctx* ctx, lp_net_plan& net, size_t oi, int batch, uint8_t* ws, cudaStream_t st);
 
 // kernels implemented per translation unit (host launchers)
 int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, void* workspace,

@@ -864,6 +864,26 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                     ok2 = false;
             return ok2 ? (int)oi + 1 : -1;
         };
+        // whole C2f body (bottleneck 3x3 chain + cv2) in one kernel, intermediates in shared memory (c2f_mma.cu)
+        if (ctx->use_tc && ctx->use_mma && ctx->use_c2f && op.kind == LP_OP_CONV && op.ksize == 3 && op.stride == 1 && op.cin == op.cout &&
+            !(ctx->probe_net == net_id && ctx->probe_op >= (int)oi && ctx->probe_op <= (int)oi + 4)) {
+            const int n_cov = lp_c2f_fused_try(ctx, net, oi, batch, ws, st);
+            if (n_cov < 0) return n_cov;
+            if (n_cov > 0) {
+                LP_LAUNCH_OK(ctx);
+                net.last_path[oi] = 5;
+                for (int j = 1; j < n_cov; ++j) {
+                    net.last_path[oi + j] = 3;
+                    if (probe_all && (int)(oi + j) < LP_PROBE_RING) {     // absorbed ops: an empty interval, so every slot of the pass is recorded
+                        LP_CUDA(cudaEventRecord(ctx->probe_ev[2 * (oi + j)], st));
+                        LP_CUDA(cudaEventRecord(ctx->probe_ev[2 * (oi + j) + 1], st));
+                        if (ctx->probe_n < (int)(oi + j) + 1) ctx->probe_n = (int)(oi + j) + 1;
+                    }
+                }
+                oi += n_cov - 1;
+                continue;
+            }
+        }
         // warp-level tensor-core path for the small-channel layers (conv_mma.cu)
         if (ctx->use_tc && ctx->use_mma && op.kind == LP_OP_CONV && op.flags == 0 && op.out_seg_len == 0 && p.out_cstride == 1 &&
             p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16 && op.cin <= 40 && op.cout <= 24 && (size_t)op.cout * 8 == (size_t)(op.cout / 8) * 64) {
