@@ -18,6 +18,7 @@
 // garbage that only ever reaches the outer rings (ring k is dead after conv k), never the centre.  A-fragments are
 // ldmatrix rows of [plane][8-channel chunk][pixel][16 B], so im2col is an address offset, as in conv_mma.cu.
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -63,7 +64,7 @@ __device__ __forceinline__ float2 join_pair(uint32_t hi, uint32_t lo) {
     return make_float2(a.x + b.x, a.y + b.y);
 }
 
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ float silu(float v) { return lp_silu(v); }
 
 // One 3x3 conv (8*C8 -> 8*C8 channels) on MS segments of 16 flat pixels starting at f0[m].  in_hi = shared-memory address of
 // chunk 0 of the conv's input frame (hi plane; lo plane `plane_stride` further), wf = the conv's weight fragments
@@ -196,7 +197,6 @@ __global__ void __launch_bounds__(NW * 32) c2f_fused_kernel(const C2fParams p) {
     __syncthreads();
 
     const int per_img = p.tiles_x * p.tiles_y;
-    constexpr int MS = 2;                      // segments per work item: one weight-fragment load feeds both, and their MMA chains interleave
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int img = tile / per_img, tr = tile - img * per_img;
@@ -233,10 +233,11 @@ __global__ void __launch_bounds__(NW * 32) c2f_fused_kernel(const C2fParams p) {
             const uint4* wf = wf3 + (k - 1) * KS3 * NT * 32;
             const float* bs = bias + (k - 1) * 8 * C8;
             const int f_begin = k * P, n_seg = ((R - 2 * k) * P + 15) / 16;
-            for (int item = warp; item * MS < n_seg; item += NW) {
+            auto stage_item = [&](auto ms_c, int seg0) {
+                constexpr int MS = decltype(ms_c)::value;
                 int f0[MS];
 #pragma unroll
-                for (int m = 0; m < MS; ++m) f0[m] = f_begin + min(item * MS + m, n_seg - 1) * 16;    // an odd tail repeats the last segment
+                for (int m = 0; m < MS; ++m) f0[m] = f_begin + (seg0 + m) * 16;
                 float acc[MS][NT][4];
                 conv3_multi<C8, P, SL, CHUNK, MS>(in_hi, in_pl, wf, bs, f0, lane, acc);
 #pragma unroll
@@ -261,7 +262,12 @@ __global__ void __launch_bounds__(NW * 32) c2f_fused_kernel(const C2fParams p) {
                             *reinterpret_cast<uint32_t*>(out_f + C8 * CHUNK + o) = inside ? lo : 0u;
                         }
                     }
-            }
+            };
+            // every warp takes a contiguous share of the stage's segments (sizes differ by at most one), two at a time
+            int sg = (warp * n_seg) / NW;
+            const int sg_end = ((warp + 1) * n_seg) / NW;
+            for (; sg + 1 < sg_end; sg += 2) stage_item(std::integral_constant<int, 2>{}, sg);
+            if (sg < sg_end) stage_item(std::integral_constant<int, 1>{}, sg);
             __syncthreads();
         }
 
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(NW * 32) c2f_fused_kernel(const C2fParams p) {
             const uint8_t* res_f = NB == 1 ? fr_y + C8 * CHUNK : fr_2;
             constexpr int res_pl = NB == 1 ? 2 * C8 * CHUNK : C8 * CHUNK;
             const int lm = lane >> 3, lj = (lane & 7) + 8 * (lm & 1);
+            constexpr int MS = (TH / NW >= 2) ? 2 : 1;      // centre rows per work item: every warp busy, two MMA chains when rows allow
             static_assert(TH % MS == 0, "tile rows per work item");
             for (int r0 = warp * MS; r0 < TH; r0 += NW * MS) {
                 int f0[MS];

@@ -104,6 +104,17 @@ __device__ __forceinline__ void lin_coef(int d, double scale, int n, bool clamp_
     c1 = (int)rintf(__fmul_rn(f, 2048.f));
 }
 
+// ---- SiLU / sigmoid in five instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL).  __expf / __fdividef wrap the same two MUFU
+// ops in range fix-ups (3 more instructions per value) that cannot change the result here: where ex2 would be denormal,
+// 1 + e rounds to 1 either way.  The epilogues apply this to every activation of the network.
+__device__ __forceinline__ float lp_sigmoid(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
+__device__ __forceinline__ float lp_silu(float v) { return v * lp_sigmoid(v); }
+
 // ---- split-f16 helpers -------------------------------------------------------
 __device__ __forceinline__ float split_load(const __half* hi, const __half* lo, size_t i) {
     return __half2float(hi[i]) + __half2float(lo[i]);
@@ -139,6 +150,7 @@ struct ConvParams {
 // warp-level tensor-core path for the small-channel layers (conv_mma.cu): returns 1 if it ran the op (and, when *fused_next,
 // the 1x1 conv that follows it), 0 if the shape is not covered
 int lp_conv_mma_try(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st);
+int lp_stem_mma_try(lp_ctx* ctx, const ConvParams& p, cudaStream_t st);
 
 // fused C2f body (c2f_mma.cu): number of plan ops covered starting at op `oi` (0: pattern / shape not covered, < 0: error)
 int lp_c2f_fused_try(lp_ctx* ctx, lp_net_plan& net, size_t oi, int batch, uint8_t* ws, cudaStream_t st);

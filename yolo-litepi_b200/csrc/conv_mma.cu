@@ -38,7 +38,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 __device__ __forceinline__ float act1(float v, int act) {
-    if (act == LP_ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
+    if (act == LP_ACT_SILU) return lp_silu(v);
     if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
     if (act == LP_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
     return v;
@@ -255,6 +255,131 @@ __global__ void __launch_bounds__(MM_THREADS) conv_mma_kernel(const ConvParams p
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stem: 3x3 s2 conv on the u8 letterboxed image (model.ncnn.param:5, /255 of e2e.py:228 fused) on the warp-level tensor cores.
+// The fp32-FMA kernel that ran it spent ~940 thread instructions per output pixel for 216 FMAs (ncu: 88 % issue slots at 14 % of
+// DRAM throughput, profiles/r2_ncu_stages.txt).  As a GEMM the layer is M = pixels, N = 8 / 16, K = 27 -- what made a first
+// MMA version slower was gathering 27 scattered bytes per pixel into fragments.  The gather disappears with the right K order:
+// for one output pixel and one filter row ky, the 9 inputs (kx, c) are 9 CONTIGUOUS bytes of the NHWC u8 image, starting at byte
+// 6*ox - 3 of input row 2*oy + ky - 1.  K is laid out as three runs of 10: k = 10*ky + j, byte 6*ox - 4 + j of that row, where
+// j = 0 (the last channel of the pixel before the window) carries a zero weight; k = 30, 31 are zero too.  Every (k, k+1) pair
+// of an A fragment is then one ALIGNED 16-bit shared-memory load, and u8 -> f16 is a byte permute into 0x64xx (= 1024 + x) and
+// one HSUB2.  A is exact in f16 (integers 0..255), so the product needs two MMAs per k-step, not three: A x Bhi + A x Blo, with
+// B = w * 2^12 / 255 split into hi | lo (the scale keeps the lo halves out of the f16 subnormals) and the fp32 accumulator
+// rescaled by 2^-12 before bias and SiLU.  Zero padding = zero bytes (mean 0, std 1 only; other stems use the generic kernel).
+constexpr int ST_TH = 8, ST_TW = 64;                   // output tile: one row per warp, four 16-pixel segments per row
+constexpr int ST_PR = 2 * ST_TH + 1;                   // patch rows
+constexpr int ST_PITCH = 416;                          // bytes per patch row: 16 (alignment lead) + 6 * 64 + 6, rounded up to 16
+
+template <int NT>
+__global__ void __launch_bounds__(256) stem_mma_kernel(const ConvParams p, int tiles_x, int tiles_y) {
+    __shared__ __align__(16) uint8_t s_patch[ST_PR * ST_PITCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int img = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
+    const int oy0 = ty * ST_TH, ox0 = tx * ST_TW;
+    const int row_bytes = p.W * 3;
+    // ---- patch: rows 2*oy0 - 1 .. 2*oy0 + 15, bytes [6*ox0 - 16, 6*ox0 - 16 + PITCH) of each (16-byte chunks: inside the row or zeros)
+    {
+        const uint8_t* base = (const uint8_t*)p.in.base + (long long)img * p.in.img;
+        const uint32_t pb = smem_addr(s_patch);
+        constexpr int CPR = ST_PITCH / 16;
+        for (int e = tid; e < ST_PR * CPR; e += 256) {
+            const int r = e / CPR, c = e - r * CPR;
+            const int iy = 2 * oy0 - 1 + r, off = 6 * ox0 - 16 + 16 * c;
+            const bool valid = (unsigned)iy < (unsigned)p.H && off >= 0 && off + 16 <= row_bytes;
+            cp16(pb + (uint32_t)(r * ST_PITCH + 16 * c), base + (valid ? (long long)iy * row_bytes + off : 0), valid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ---- weight fragments (while the patch is in flight): B[k][n], k = 10 * ky + j, j = 1 + 3 * kx + c
+    uint32_t bh[2][NT][2], bl[2][NT][2];
+    const float wscale = 4096.f / 255.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float x[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int k = 16 * ks + 8 * h + 2 * tq + i, ky = k / 10, j = k - 10 * ky;
+                    const int n = nt * 8 + g;
+                    x[i] = (k < 30 && j >= 1 && n < p.cout) ? __ldg(p.w + ((ky * 3 + (j - 1) / 3) * 3 + (j - 1) % 3) * p.cout + n) * wscale : 0.f;
+                }
+                split2(x[0], x[1], bh[ks][nt][h], bl[ks][nt][h]);
+            }
+    // byte offset of this lane's (k, k+1) pair inside a pixel's window, per (k-step, half); pads re-read pair 0
+    int koff[2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 16 * ks + 8 * h + 2 * tq, ky = k / 10, j = k - 10 * ky;
+            koff[ks][h] = k < 30 ? ky * ST_PITCH + j : 0;
+        }
+    float bias[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        bias[nt][0] = nt * 8 + tq * 2 < p.cout ? __ldg(p.bias + nt * 8 + tq * 2) : 0.f;
+        bias[nt][1] = nt * 8 + tq * 2 + 1 < p.cout ? __ldg(p.bias + nt * 8 + tq * 2 + 1) : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int oy = oy0 + warp;
+    if (oy >= p.Ho) return;
+    const uint8_t* rowp = s_patch + (2 * warp) * ST_PITCH + 12;       // window of local pixel 0, filter row 0, j = 0
+    const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
+    __half* outp = (__half*)p.out.base + (long long)img * p.out.img + (long long)oy * p.Wo * p.out.C + p.out.coff + tq * 2;
+#pragma unroll
+    for (int sg = 0; sg < ST_TW / 16; ++sg) {
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+        const uint8_t* px0 = rowp + 6 * (16 * sg + g);                // rows g; rows g + 8 are 48 bytes further
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t a[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int hr = 0; hr < 2; ++hr) {
+                    const uint32_t raw = *reinterpret_cast<const uint16_t*>(px0 + koff[ks][h] + 48 * hr);
+                    uint32_t v;
+                    asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(v) : "r"(raw), "r"(0x64646464u));     // {x0, 0x64, x1, 0x64} = half2(1024 + x0, 1024 + x1)
+                    const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&v), k1024);
+                    a[2 * h + hr] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                mma16816(acc[nt], a, bh[ks][nt][0], bh[ks][nt][1]);
+                mma16816(acc[nt], a, bl[ks][nt][0], bl[ks][nt][1]);
+            }
+        }
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr) {
+            const int ox = ox0 + 16 * sg + g + 8 * hr;
+            if (ox >= p.Wo) continue;
+            __half* o = outp + (long long)ox * p.out.C;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                if (nt * 8 + tq * 2 >= p.cout) continue;
+                const float x0 = act1(fmaf(acc[nt][2 * hr], 1.f / 4096.f, bias[nt][0]), p.act);
+                const float x1 = act1(fmaf(acc[nt][2 * hr + 1], 1.f / 4096.f, bias[nt][1]), p.act);
+                uint32_t hi, lo;
+                split2(x0, x1, hi, lo);
+                *reinterpret_cast<uint32_t*>(o + nt * 8) = hi;
+                *reinterpret_cast<uint32_t*>(o + p.out.plane + nt * 8) = lo;
+            }
+        }
+    }
+}
+
 template <int KS, int STRIDE, int CH, int NT, bool POST>
 int launch_mma(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st) {
     const int tiles_x = (p.Wo + MM_TW - 1) / MM_TW, tiles_y = (p.Ho + MM_TH - 1) / MM_TH;
@@ -290,4 +415,20 @@ int lp_conv_mma_try(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cu
     LP_MMA_CASE(1, 1, 3, 3)      // v2 model.2.cv1 alone
 #undef LP_MMA_CASE
     return 0;
+}
+
+// u8 stem (3x3 s2, 3 -> 8 / 16 channels, x / 255, zero mean / unit std) on the warp-level tensor cores; 0 if the shape is not covered
+int lp_stem_mma_try(lp_ctx* ctx, const ConvParams& p, cudaStream_t st) {
+    if (p.in.fmt != LP_FMT_U8 || p.out.fmt != LP_FMT_SPLIT16 || p.ksize != 3 || p.stride != 2 || p.cin != 3) return 0;
+    if (p.cout != 8 && p.cout != 16) return 0;
+    if (p.in_scale_mean != 0.f || p.in_scale_std != 1.f || p.res.base || p.seg_len != 0 || p.out_cstride != 1 || p.out.coff % 8) return 0;
+    // 16-byte chunks of an image row: the rows and the images must start on 16-byte boundaries
+    if ((p.W * 3) % 16 || (p.in.img % 16) || ((uintptr_t)p.in.base % 16) || p.W % 2 || p.H % 2) return 0;
+    const int tiles_x = (p.Wo + ST_TW - 1) / ST_TW, tiles_y = (p.Ho + ST_TH - 1) / ST_TH;
+    if (p.n_img > 65535 || tiles_y > 65535) return 0;
+    dim3 grid(tiles_x, tiles_y, p.n_img);
+    if (p.cout == 8) stem_mma_kernel<1><<<grid, 256, 0, st>>>(p, tiles_x, tiles_y);
+    else stem_mma_kernel<2><<<grid, 256, 0, st>>>(p, tiles_x, tiles_y);
+    (void)ctx;
+    return 1;
 }

@@ -8,10 +8,10 @@
 #include "common.cuh"
 
 __device__ __forceinline__ float act_apply(float v, int act) {
-    if (act == LP_ACT_SILU) return v / (1.f + __expf(-v));
+    if (act == LP_ACT_SILU) return lp_silu(v);
     if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
     if (act == LP_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
-    if (act == LP_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    if (act == LP_ACT_SIGMOID) return lp_sigmoid(v);
     return v;
 }
 
@@ -904,6 +904,11 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                 if (r == 1 && post_idx >= 0) { ++oi; net.last_path[oi] = 3; }
                 continue;
             }
+        }
+        if (ctx->use_tc && ctx->use_mma && op.kind == LP_OP_STEM_U8 && op.flags == 0 && lp_stem_mma_try(ctx, p, st)) {
+            LP_LAUNCH_OK(ctx);
+            net.last_path[oi] = 4;
+            continue;
         }
         if ((op.kind == LP_OP_STEM_U8 || op.kind == LP_OP_CONV) && net.small_slot.size() > oi && net.small_slot[oi] >= 0 && op.flags == 0 &&
             (p.res.base == nullptr || (p.res.fmt == LP_FMT_SPLIT16 && p.res.coff % 8 == 0)) && p.seg_len == 0 &&

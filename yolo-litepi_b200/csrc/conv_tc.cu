@@ -177,7 +177,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 
 __device__ __forceinline__ float act_fn(float v, int act) {
-    if (act == LP_ACT_SILU) return v / (1.f + __expf(-v));
+    if (act == LP_ACT_SILU) return lp_silu(v);
     if (act == LP_ACT_RELU) return fmaxf(v, 0.f);
     return v;
 }
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
                 if (pass == (p.res_first ? 1 : 0)) {
                 if (p.act == LP_ACT_SILU) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
+                    for (int i = 0; i < 16; ++i) f[i] = lp_silu(f[i]);
                 } else if (p.act == LP_ACT_RELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
