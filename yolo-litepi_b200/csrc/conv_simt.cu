@@ -650,6 +650,32 @@ __global__ void resample_copy8_kernel(ConvParams p) {
     *reinterpret_cast<uint4*>(d) = __ldg(reinterpret_cast<const uint4*>(s));
 }
 
+// Nearest x2 upsample, one thread per SOURCE chunk (16 bytes = 8 channels of one plane of one input pixel): one load, four
+// stores, and the index arithmetic (five divisions by runtime divisors: most of the per-output-chunk kernel above, which ran
+// at 2 TB/s) is paid once per four output chunks.  Consecutive threads cover the consecutive chunks of a pixel row.
+__global__ void upsample2x8_kernel(ConvParams p) {
+    const unsigned cpp = (unsigned)p.cout >> 3;
+    const unsigned total = 2u * (unsigned)p.n_img * (unsigned)p.H * (unsigned)p.W * cpp;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const unsigned ch = i % cpp;
+    unsigned r = i / cpp;
+    const unsigned ix = r % (unsigned)p.W; r /= (unsigned)p.W;
+    const unsigned iy = r % (unsigned)p.H; r /= (unsigned)p.H;
+    const unsigned img = r % (unsigned)p.n_img;
+    const unsigned plane = r / (unsigned)p.n_img;
+    const __half* s = (const __half*)p.in.base + (long long)plane * p.in.plane + (long long)img * p.in.img +
+                      ((long long)iy * p.W + ix) * p.in.C + p.in.coff + ch * 8;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(s));
+    __half* d = (__half*)p.out.base + (long long)plane * p.out.plane + (long long)img * p.out.img +
+                ((long long)(2 * iy) * p.Wo + 2 * ix) * p.out.C + p.out.coff + ch * 8;
+    const long long row = (long long)p.Wo * p.out.C;
+    *reinterpret_cast<uint4*>(d) = v;
+    *reinterpret_cast<uint4*>(d + p.out.C) = v;
+    *reinterpret_cast<uint4*>(d + row) = v;
+    *reinterpret_cast<uint4*>(d + row + p.out.C) = v;
+}
+
 // max pool on split-f16, 8 channels per thread.  max(hi+lo) is taken on the reconstructed fp32 values.
 __global__ void maxpool8_kernel(ConvParams p) {
     const int cpp = p.cout >> 3;
@@ -999,7 +1025,9 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
             p.stride = op.kind == LP_OP_UPSAMPLE2 ? 2 : 1;
             const bool v8 = p.in.fmt == LP_FMT_SPLIT16 && p.out.fmt == LP_FMT_SPLIT16 && p.cout % 8 == 0 &&
                             p.in.coff % 8 == 0 && p.out.coff % 8 == 0 && p.out_cstride == 1 && p.seg_len == 0;
-            if (v8 && total / 4 < (1ll << 31)) resample_copy8_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(p);
+            if (v8 && op.kind == LP_OP_UPSAMPLE2 && total / 16 < (1ll << 31) && p.Ho == 2 * p.H && p.Wo == 2 * p.W)
+                upsample2x8_kernel<<<(unsigned)((total / 16 + 255) / 256), 256, 0, st>>>(p);
+            else if (v8 && total / 4 < (1ll << 31)) resample_copy8_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, st>>>(p);
             else resample_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
             break;
         }

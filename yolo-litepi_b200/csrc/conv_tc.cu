@@ -78,6 +78,7 @@ struct TcParams {
     int n_units, upb, unit_bytes;   // K units (tap x channel block) per tile, units per weight block, bytes per unit
     int w_stages, stage_bytes, resident;
     int patch_stages, acc_stages;
+    int ld_depth;              // patch tiles a loader thread keeps in flight before it waits for (and publishes) the oldest
     int n_mma, mtab_bytes;     // MMA issue table: one uint2 per tcgen05.mma of a tile
     int fills_per_tile;        // streaming weights: n_kb / w_stages (stage pattern repeats every tile)
     int epi_pitch, epi_bytes;  // epilogue staging: bytes per pixel row (+16 pad) and total (0 = direct stores)
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         asm volatile("griddepcontrol.wait;" ::: "memory");      // activations of the previous layer are complete and visible
         // Up to `depth` tiles are in flight per thread (one cp.async group each): a tile costs a full
         // L2/HBM round trip, so the loader must not wait for tile i before issuing tile i+1.
-        const int depth = p.patch_stages - 1 < 4 ? p.patch_stages - 1 : 4;
+        const int depth = p.ld_depth;
         int issued = 0, arrived = 0;
         long long t_wait_empty = 0, t_issue = 0, t_wait_cp = 0;
         const __half* in_c = p.in + p.in_coff;
@@ -964,7 +965,19 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         ctx->attr_set |= 1;
     }
+    // Grid: one persistent CTA per SM.  (Tried: fewer CTAs with >= 4 / 6 / 10 tiles each on the layers with few tiles per SM, so that the
+    // SMs left free run the other batches in flight: throughput unchanged at 4 and 6, -8 % at 10, single-batch latency +9 .. +46 %.)
     const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
+    {   // loader look-ahead: deep for the long HBM-bound layers; CTAs that only see a few tiles publish the first one early
+        static int f = -2; if (f == -2) { const char* e = getenv("LP_TC_DEPTH"); f = e ? atoi(e) : -1; }
+        const int tiles_per_cta = (p.n_tiles + grid - 1) / grid;
+        // measured (tools/op_times.py): publishing every tile as soon as it has landed (0) wins wherever the loaders are not the
+        // bound; only the long 1x1 layers, whose tile period is close to the loaders' issue + latency time, want look-ahead
+        int d = f >= 0 ? f : ((tiles_per_cta > 8 && p.ksize == 1) ? 4 : 0);
+        if (d > p.patch_stages - 1) d = p.patch_stages - 1;
+        if (d > 4) d = 4;
+        p.ld_depth = d;
+    }
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_PLAN"); f = e ? atoi(e) : 0; }
       if (f) fprintf(stderr, "conv_tc plan: %dx%d s%d cin %d cout %d(+%d) %dx%d | %s kb_ch %d units %d upb %d blocks %d w_stages %d stage %d B | patches %d x %zu B | epi %d B | acc %d x %d cols | tiles %d grid %d smem %zu\n",
                      op.ksize, op.ksize, op.stride, op.cin, nb, n0, p.H, p.W, p.resident ? "resident" : "stream", p.kb_ch, p.n_units, p.upb, p.n_kb,
