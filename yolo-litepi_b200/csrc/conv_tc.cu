@@ -37,6 +37,7 @@
 // layers are HBM/latency-bound, so tiles i+1.. load and tile i-1 drains while tile i is in the tensor core.
 // Consecutive launches are chained with programmatic dependent launch (griddepcontrol).
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 #include <type_traits>
 
@@ -89,6 +90,11 @@ struct TcParams {
                                // B: Alo x Bhi -> columns [2*cout, 3*cout)); 0: one warp issues both, Alo x Bhi accumulates into [0, cout)
     unsigned magic_chunks, magic_pitch;   // ceil(2^32 / n) for division by n_chunks / pitch
     long long total_pix;       // 1x1: n_img*H*W
+    int use_tma;               // 1: patches arrive by TMA tensor copies (one elected loader thread), 0: cp.async by the loader warps
+    int plane_bytes;           // bytes of one plane (hi or lo) of a patch stage
+    int tma_box_bytes;         // bytes one tensor copy delivers (one 8-channel chunk of one plane of a patch)
+    int max_batch;             // the lo plane of image i is image max_batch + i of the tensor map
+    alignas(64) CUtensorMap tmap;   // 3x3: {C, W, H, 2*max_batch} box {8, 10, 18, 1};  1x1: {C, 2*max_batch*H*W} box {8, 128}
     int dbg_flags;             // debugging (env LP_TC_DEBUG): 1 = loaders skip copies, 2 = epilogue skips math/stores, 4 = weights loaded once
     long long* dbg;            // optional: per-role cycle counters of CTA 0 (tools/op_times.py --tc-timing)
 };
@@ -116,6 +122,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
     const uint32_t n = valid ? 16u : 0u;       // src-size 0 -> 16 bytes of zeros (halo / padding)
@@ -342,7 +356,7 @@ __device__ __forceinline__ void mma_role(const TcParams& p, const uint32_t tmem_
 
 // smem carve-up: [barriers 512 B][patch ring][weight stages]
 template <bool DBG, bool SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);        // [MAX_WST]
     uint64_t* w_empty = w_full + MAX_WST;                        // [MAX_WST]
@@ -355,7 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + 2);
     uint8_t* patch0 = smem + 512;
     const int n_chunks = p.cin >> 3;
-    const uint32_t plane_bytes = (uint32_t)n_chunks * p.slots_p * 16;
+    const uint32_t plane_bytes = (uint32_t)p.plane_bytes;
     const uint32_t patch_bytes = 2 * plane_bytes;
     uint8_t* wst = patch0 + (size_t)p.patch_stages * patch_bytes;
     uint32_t* tab = reinterpret_cast<uint32_t*>(wst + (size_t)p.w_stages * p.stage_bytes);
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
     if (threadIdx.x == 0) {
         const uint32_t n_issuers = SPLIT ? 2 : 1;      // every MMA-issuing warp commits to the barriers it consumes through
         for (int s = 0; s < p.w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], n_issuers); }
-        for (int s = 0; s < MAX_PST; ++s) { mbar_init(&patch_full[s], LOADER_THREADS); mbar_init(&patch_empty[s], n_issuers); }
+        for (int s = 0; s < MAX_PST; ++s) { mbar_init(&patch_full[s], p.use_tma ? 1 : LOADER_THREADS); mbar_init(&patch_empty[s], n_issuers); }
         for (int s = 0; s < MAX_AST; ++s) { mbar_init(&acc_full[s], n_issuers); mbar_init(&acc_empty[s], EPI_WARPS * 32); }
         for (int s = 0; s < 2; ++s) { mbar_init(&stage_full[s], EPI_WARPS * 32); mbar_init(&stage_empty[s], STORE_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -447,6 +461,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         // instructions (bounds test, one multiply-add, two cp.async).
         const int lt = threadIdx.x - W_LOADER0 * 32;
         const int items_per_plane = n_chunks * p.slots;
+        if (p.use_tma) {
+            // ---- TMA variant: ONE thread issues 2 * n_chunks tensor copies per tile (a chunk = the 8-channel slice of the halo patch,
+            // [18][10][16 B] for a 3x3 tile, [128][16 B] for a 1x1 tile; out-of-image coordinates are zero-filled by the copy engine =
+            // the conv's padding); the patch barrier counts the bytes (expect_tx), so the other loader threads have nothing to do.
+            if (lt == 0) {
+                const void* tmap = &p.tmap;
+                asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                uint32_t ps = 0, ps_phase = 0;
+                int it = 0;
+                const uint32_t chunk_bytes = (uint32_t)p.slots_p * 16;
+                const int c_base = p.in_coff;
+                for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                    if (it >= p.patch_stages) mbar_wait(&patch_empty[ps], ps_phase ^ 1);
+                    const TileCoord tc = tile_coord(p, tile);
+                    const uint32_t dst0 = smem_u32(patch0 + (size_t)ps * patch_bytes);
+                    mbar_expect_tx(&patch_full[ps], 2u * (uint32_t)n_chunks * (uint32_t)p.tma_box_bytes);
+                    if (p.ksize == 1) {
+                        const long long lo_pix = (long long)p.max_batch * hw_in;
+                        for (int pl = 0; pl < 2; ++pl)
+                            for (int ch = 0; ch < n_chunks; ++ch)
+                                tma_load_2d(dst0 + (uint32_t)pl * plane_bytes + (uint32_t)ch * chunk_bytes, tmap, c_base + 8 * ch,
+                                            (int)(tc.pix0 + pl * lo_pix), &patch_full[ps]);
+                    } else {
+                        for (int pl = 0; pl < 2; ++pl)
+                            for (int ch = 0; ch < n_chunks; ++ch)
+                                tma_load_4d(dst0 + (uint32_t)pl * plane_bytes + (uint32_t)ch * chunk_bytes, tmap, c_base + 8 * ch,
+                                            tc.ox0 - 1, tc.oy0 - 1, pl * p.max_batch + tc.img, &patch_full[ps]);
+                    }
+                    if (++ps == (uint32_t)p.patch_stages) { ps = 0; ps_phase ^= 1; }
+                }
+            }
+        } else {
         if (p.ksize == 3) {
             for (int slot = lt; slot < p.slots; slot += LOADER_THREADS) {
                 int py, px;
@@ -538,6 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcParams p
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (; arrived < issued; ++arrived) mbar_arrive(&patch_full[arrived % p.patch_stages]);
+        }
     } else if (warp == W_PRODUCER) {
         // ================= weight producer (bulk TMA) =================
         if (lane == 0) {
@@ -862,7 +910,16 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         const int ky = t / 3, kx = t % 3;
         p.tap_off[t] = op.ksize == 1 ? 0 : op.stride == 1 ? ky * p.pitch + kx : ((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1);
     }
-    p.slots_p = p.slots + ((9 - (p.slots & 7)) & 7);                 // == 1 (mod 8): conflict-free chunk stride
+    // Patch loads by TMA tensor copies (3x3 stride 1 and 1x1; the stride-2 phase split keeps cp.async).  LP_TC_TMA: 0 off, 1 3x3 only,
+    // 2 1x1 only, 3 both (default).
+    { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_TMA"); f = e ? atoi(e) : 3; }
+      p.use_tma = ((op.ksize == 3 && op.stride == 1 && (f & 1)) || (op.ksize == 1 && (f & 2))) ? 1 : 0; }
+    if (p.use_tma && (p.dbg_flags & 1)) p.use_tma = 0;
+    // chunk stride: == 1 (mod 8) slots keeps the cp.async writes conflict-free; a tensor copy needs a 128-byte aligned destination
+    p.slots_p = p.use_tma ? (p.slots + 7) / 8 * 8 : p.slots + ((9 - (p.slots & 7)) & 7);
+    p.plane_bytes = (op.cin / 8) * p.slots_p * 16;
+    p.tma_box_bytes = p.slots * 16;
+    p.max_batch = net.max_batch;
     p.magic_chunks = magic_u32(op.cin / 8);
     p.magic_pitch = magic_u32(p.pitch);
     const size_t patch_bytes = (size_t)2 * (op.cin / 8) * p.slots_p * 16;
@@ -968,6 +1025,26 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     // Grid: one persistent CTA per SM.  (Tried: fewer CTAs with >= 4 / 6 / 10 tiles each on the layers with few tiles per SM, so that the
     // SMs left free run the other batches in flight: throughput unchanged at 4 and 6, -8 % at 10, single-batch latency +9 .. +46 %.)
     const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
+    if (p.use_tma) {
+        // the tensor map is a view of the whole input buffer; the lo plane is image max_batch + i (make_ref: plane = max_batch images)
+        CUresult cr;
+        if (op.ksize == 1) {
+            const cuuint64_t dims[2] = {(cuuint64_t)ib.c, (cuuint64_t)2 * net.max_batch * ib.h * ib.w};
+            const cuuint64_t strides[1] = {(cuuint64_t)ib.c * 2};
+            const cuuint32_t box[2] = {8, (cuuint32_t)TILE_M}, es[2] = {1, 1};
+            cr = cuTensorMapEncodeTiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.in), dims, strides, box, es,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t dims[4] = {(cuuint64_t)ib.c, (cuuint64_t)ib.w, (cuuint64_t)ib.h, (cuuint64_t)2 * net.max_batch};
+            const cuuint64_t strides[3] = {(cuuint64_t)ib.c * 2, (cuuint64_t)ib.w * ib.c * 2, (cuuint64_t)ib.image_bytes};
+            const cuuint32_t box[4] = {8, (cuuint32_t)p.pitch, (cuuint32_t)(TCT_H + 2), 1}, es[4] = {1, 1, 1, 1};
+            cr = cuTensorMapEncodeTiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.in), dims, strides, box, es,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        LP_CHECK(cr == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed (%d) for %dx%d cin %d", (int)cr, op.ksize, op.ksize, op.cin);
+    }
     {   // loader look-ahead: deep for the long HBM-bound layers; CTAs that only see a few tiles publish the first one early
         static int f = -2; if (f == -2) { const char* e = getenv("LP_TC_DEPTH"); f = e ? atoi(e) : -1; }
         const int tiles_per_cta = (p.n_tiles + grid - 1) / grid;
