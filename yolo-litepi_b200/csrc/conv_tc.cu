@@ -90,6 +90,8 @@ struct TcParams {
                                // B: Alo x Bhi -> columns [2*cout, 3*cout)); 0: one warp issues both, Alo x Bhi accumulates into [0, cout)
     unsigned magic_chunks, magic_pitch;   // ceil(2^32 / n) for division by n_chunks / pitch
     long long total_pix;       // 1x1: n_img*H*W
+    int a_sw128;               // 1x1 layers with cin % 64 == 0 (TMA only): A tiles are [64-channel block][128 pixels][128 B] in the
+                               // SWIZZLE_128B K-major layout -- the tensor copy moves whole 128-byte pixel rows instead of 16-byte chunks
     int use_tma;               // 1: patches arrive by TMA tensor copies (one elected loader thread), 0: cp.async by the loader warps
     int plane_bytes;           // bytes of one plane (hi or lo) of a patch stage
     int tma_box_bytes;         // bytes one tensor copy delivers (one 8-channel chunk of one plane of a patch)
@@ -135,10 +137,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
     const uint32_t n = valid ? 16u : 0u;       // src-size 0 -> 16 bytes of zeros (halo / padding)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // SmemDescriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | no swizzle
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 0) {
+    // SmemDescriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout type [61,64)
+    // (0 = no swizzle, 2 = SWIZZLE_128B)
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -223,21 +226,24 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
 // [2*cout, 3*cout)) only selects operand values.  `sel` must be a value ptxas knows to be warp-uniform (it comes from a
 // redux.sync): with a second copy of the loops, or anything derived from threadIdx in them, ptxas leaves the uniform
 // datapath (R2UR + vector adds per tcgen05.mma: measured 2x slower).
-template <int which, bool DBG>
+template <int which, bool DBG, bool SW>
 __device__ __forceinline__ void mma_role(const TcParams& p, const uint32_t tmem_base, const bool pure, uint8_t* const patch0, uint8_t* const wst,
                                          const uint32_t plane_bytes, const uint32_t patch_bytes, uint64_t* const w_full, uint64_t* const w_empty,
                                          uint64_t* const patch_full, uint64_t* const patch_empty, uint64_t* const acc_full,
                                          uint64_t* const acc_empty, const uint32_t sel) {
     const uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * p.cout) >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
     const uint32_t idesc1 = (1u << 4) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-    const uint32_t lbo_a = (uint32_t)p.slots_p * 16, sbo_a = (uint32_t)p.pitch * 16;
+    const uint32_t lbo_a = SW ? 16u : (uint32_t)p.slots_p * 16, sbo_a = SW ? 1024u : (uint32_t)p.pitch * 16;
     const uint32_t lbo_b = (uint32_t)p.cout * 32, sbo_b = 128;            // chunk stride = [hi|lo] rows
-    const uint64_t da_base = umma_desc(0, lbo_a, sbo_a), db_base = umma_desc(0, lbo_b, sbo_b);
+    const uint64_t da_base = umma_desc(0, lbo_a, sbo_a, SW ? 2u : 0u), db_base = umma_desc(0, lbo_b, sbo_b);
     const uint32_t da_hi = (uint32_t)(da_base >> 32), da_lo0 = (uint32_t)da_base;
     const uint32_t db_hi = (uint32_t)(db_base >> 32);
     const uint32_t b016 = (uint32_t)db_base + (smem_u32(wst) >> 4);
     const uint32_t plane16 = plane_bytes >> 4;
-    const uint32_t a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
+    // A per K-step (16 channels): two chunk planes further; swizzled rows: 32 bytes further inside the 128-byte row, and
+    // a_unit16 more at the end of each 64-channel block (the next block is 16 KB further)
+    const uint32_t a_step16 = SW ? 2u : (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
+    constexpr uint32_t a_unit16 = SW ? (16384u >> 4) - 8u : 0u;
     const uint32_t patch016 = da_lo0 + (smem_u32(patch0) >> 4), patch_stride16 = patch_bytes >> 4;
     const int ksteps = p.kb_ch >> 4, ktot = p.cin >> 4, taps = p.ksize * p.ksize;
     const uint32_t leader = elect_one() ? 1u : 0u;
@@ -273,7 +279,18 @@ __device__ __forceinline__ void mma_role(const TcParams& p, const uint32_t tmem_
             for (int tap = 0; tap < 9; ++tap) {
                 if (tap < taps) {
                     uint32_t a16 = patch16 + (uint32_t)p.tap_off[tap];
-                    if constexpr (which == 3) {
+                    if constexpr (SW) {                    // swizzled 1x1 tiles (never split): 64-channel blocks of four K-steps, 16 KB apart
+                        for (int cb = 0; cb < p.n_cb; ++cb) {
+                            for (int ks = 0; ks < 4; ++ks) {
+                                umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);
+                                umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);
+                                acc = 1;
+                                a16 += a_step16;
+                                b16 += b_step16;
+                            }
+                            a16 += a_unit16;
+                        }
+                    } else if constexpr (which == 3) {
                         for (int kk = 0; kk < ktot; ++kk) {
                             umma_f16_pred(d_tmem, a16, da_hi, b16, db_hi, idesc2, acc, leader);           // Ahi x [Bhi|Blo]
                             umma_f16_pred(d_tmem, a16 + plane16, da_hi, b16, db_hi, idesc1, 1, leader);   // Alo x Bhi
@@ -326,6 +343,7 @@ __device__ __forceinline__ void mma_role(const TcParams& p, const uint32_t tmem_
                                 b16 += b_step16;
                             }
                         }
+                        if constexpr (SW) a16 += a_unit16;
                         --units_left;
                         if (++u_in_blk == p.upb || units_left == 0) {
                             if (leader && !pure) umma_commit(&w_empty[st]);  // frees the weight stage once these MMAs retire
@@ -355,9 +373,9 @@ __device__ __forceinline__ void mma_role(const TcParams& p, const uint32_t tmem_
 }
 
 // smem carve-up: [barriers 512 B][patch ring][weight stages]
-template <bool DBG, bool SPLIT>
+template <bool DBG, bool SPLIT, bool SW>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem);        // [MAX_WST]
     uint64_t* w_empty = w_full + MAX_WST;                        // [MAX_WST]
     uint64_t* patch_full = w_empty + MAX_WST;                    // [MAX_PST]
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint64_t* stage_full = acc_empty + MAX_AST;                  // [2] epilogue staging tile written
     uint64_t* stage_empty = stage_full + 2;                      // [2] ... and copied out
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_empty + 2);
-    uint8_t* patch0 = smem + 512;
+    uint8_t* patch0 = smem + 1024;            // 1024-byte aligned: swizzled A tiles need it
     const int n_chunks = p.cin >> 3;
     const uint32_t plane_bytes = (uint32_t)p.plane_bytes;
     const uint32_t patch_bytes = 2 * plane_bytes;
@@ -478,7 +496,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const TileCoord tc = tile_coord(p, tile);
                     const uint32_t dst0 = smem_u32(patch0 + (size_t)ps * patch_bytes);
                     mbar_expect_tx(&patch_full[ps], 2u * (uint32_t)n_chunks * (uint32_t)p.tma_box_bytes);
-                    if (p.ksize == 1) {
+                    if (SW) {
+                        const long long lo_pix = (long long)p.max_batch * hw_in;
+                        const int n_blk = n_chunks >> 3;                       // 64-channel blocks
+                        for (int pl = 0; pl < 2; ++pl)
+                            for (int kb = 0; kb < n_blk; ++kb)
+                                tma_load_2d(dst0 + (uint32_t)pl * plane_bytes + (uint32_t)kb * 16384u, tmap, c_base + 64 * kb,
+                                            (int)(tc.pix0 + pl * lo_pix), &patch_full[ps]);
+                    } else if (p.ksize == 1) {
                         const long long lo_pix = (long long)p.max_batch * hw_in;
                         for (int pl = 0; pl < 2; ++pl)
                             for (int ch = 0; ch < n_chunks; ++ch)
@@ -619,7 +644,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // (contiguous) weight stages.
         // redux.sync: the result lives in a uniform register, so the operand selection below stays in the uniform datapath
         const uint32_t sel = SPLIT ? (uint32_t)__reduce_max_sync(0xffffffffu, warp == W_MMA2 ? 1 : 0) : 0u;
-        mma_role<SPLIT ? 1 : 3, DBG>(p, tmem_base, pure, patch0, wst, plane_bytes, patch_bytes, w_full, w_empty, patch_full, patch_empty,
+        mma_role<SPLIT ? 1 : 3, DBG, SW>(p, tmem_base, pure, patch0, wst, plane_bytes, patch_bytes, w_full, w_empty, patch_full, patch_empty,
                                      acc_full, acc_empty, sel);
     } else if (warp == W_MMA2) {
         // idle in the one-issuer kernel
@@ -930,7 +955,7 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     const int out_row_bytes = nb * (ob.fmt == LP_FMT_SPLIT16 ? 2 : 4);
     p.epi_pitch = out_row_bytes + 16;
     const size_t epi_full = (size_t)(ob.fmt == LP_FMT_SPLIT16 ? 2 : 1) * TILE_M * p.epi_pitch + TILE_M * 8;
-    const size_t total = 220 * 1024 - 512 - p.tab_bytes - p.mtab_bytes;
+    const size_t total = 220 * 1024 - 1024 - p.tab_bytes - p.mtab_bytes;
     const size_t w_all = (size_t)taps * op.cin * nb * 4;
     // Shared-memory plan.  Weights: resident if the whole layer fits beside >= 2 patch stages, else a ring
     // of 2-4 stages.  Epilogue staging
@@ -991,18 +1016,21 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     }
     if (!ok) return 0;
     p.fills_per_tile = p.resident ? 0 : p.n_kb / p.w_stages;
+    // swizzled A tiles: 1x1 layers whose K splits into 64-channel blocks (same bytes per patch stage as the chunk layout)
+    { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_SW128"); f = e ? atoi(e) : 1; }
+      p.a_sw128 = (f && p.use_tma && op.ksize == 1 && op.cin % 64 == 0 && p.kb_ch == 64) ? 1 : 0; }
     // Two issuing warps (split_mma) need a third accumulator piece per stage.  Measured (profiles/r2_notes.md): with
     // cout <= 32 (four accumulator stages of 3 * cout columns still fit the 512 TMEM columns) the 3x3 layers gain 8-10 %;
     // at cout = 64 only two stages fit and the MMA warps wait for the epilogue (conv_48: 110 -> 122 us), so those layers
     // keep one issuing warp and 2 * cout columns.  LP_TC_SPLIT=0 disables, =2 forces it wherever two stages fit.
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_SPLIT"); f = e ? atoi(e) : 1; }
-      p.split_mma = (f == 2 ? 3 * nb <= 256 : (f == 1 && nb <= 32)) ? 1 : 0; }
+      p.split_mma = (!p.a_sw128 && (f == 2 ? 3 * nb <= 256 : (f == 1 && nb <= 32))) ? 1 : 0; }
     const int acc_cols = (p.split_mma ? 3 : 2) * nb;
     p.acc_stride = (acc_cols + 31) / 32 * 32;        // [Ahi*Bhi(+Alo*Bhi) | Ahi*Blo | Alo*Bhi]
     p.acc_stages = 512 / p.acc_stride > MAX_AST ? MAX_AST : 512 / p.acc_stride;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_stages * p.acc_stride) p.tmem_cols <<= 1;
-    const size_t smem = 512 + (size_t)p.patch_stages * patch_bytes + (size_t)p.w_stages * p.stage_bytes + p.tab_bytes + p.mtab_bytes + p.epi_bytes;
+    const size_t smem = 1024 + (size_t)p.patch_stages * patch_bytes + (size_t)p.w_stages * p.stage_bytes + p.tab_bytes + p.mtab_bytes + p.epi_bytes;
 
     p.inv_hw_out = 1.0f / (float)(p.Ho * p.Wo);
     if (op.ksize == 1) {
@@ -1016,10 +1044,12 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         p.magic_tiles_x = magic_u32(p.tiles_x);
     }
     if (!(ctx->attr_set & 1)) {          // per context (= per device): the opt-in is a per-device function attribute
-        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        LP_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         ctx->attr_set |= 1;
     }
     // Grid: one persistent CTA per SM.  (Tried: fewer CTAs with >= 4 / 6 / 10 tiles each on the layers with few tiles per SM, so that the
@@ -1031,9 +1061,9 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         if (op.ksize == 1) {
             const cuuint64_t dims[2] = {(cuuint64_t)ib.c, (cuuint64_t)2 * net.max_batch * ib.h * ib.w};
             const cuuint64_t strides[1] = {(cuuint64_t)ib.c * 2};
-            const cuuint32_t box[2] = {8, (cuuint32_t)TILE_M}, es[2] = {1, 1};
+            const cuuint32_t box[2] = {p.a_sw128 ? 64u : 8u, (cuuint32_t)TILE_M}, es[2] = {1, 1};
             cr = cuTensorMapEncodeTiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.in), dims, strides, box, es,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, p.a_sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
             const cuuint64_t dims[4] = {(cuuint64_t)ib.c, (cuuint64_t)ib.w, (cuuint64_t)ib.h, (cuuint64_t)2 * net.max_batch};
@@ -1066,8 +1096,10 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = ctx->use_pdl ? 1 : 0;
     const bool dbg_kernel = p.dbg != nullptr || p.dbg_flags != 0;
-    cudaError_t e = p.split_mma ? (dbg_kernel ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, p))
-                                : (dbg_kernel ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, p));
+    cudaError_t e;
+    if (p.a_sw128) e = dbg_kernel ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true>, p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, p);
+    else if (p.split_mma) e = dbg_kernel ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, false>, p);
+    else e = dbg_kernel ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, false>, p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, false>, p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         lp_set_error("conv_tc launch failed: %s (smem %zu)", cudaGetErrorString(e), smem);
