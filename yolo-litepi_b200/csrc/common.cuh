@@ -151,6 +151,7 @@ struct ConvParams {
 // the 1x1 conv that follows it), 0 if the shape is not covered
 int lp_conv_mma_try(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st);
 int lp_stem_mma_try(lp_ctx* ctx, const ConvParams& p, cudaStream_t st);
+int lp_stem_conv_try(lp_ctx* ctx, const ConvParams& ps, const ConvParams& p, const ConvParams* post, cudaStream_t st);
 
 // fused C2f body (c2f_mma.cu): number of plan ops covered starting at op `oi` (0: pattern / shape not covered, < 0: error)
 int lp_c2f_fused_try(lp_ctx* ctx, lp_net_plan& net, size_t oi, int batch, uint8_t* ws, cudaStream_t st);

@@ -380,6 +380,223 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const ConvParams p, int t
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stem + first down-sampling conv + C2f cv1 in ONE kernel (model.ncnn.param:5-8: 3x3 s2 3->8, 3x3 s2 8->16, 1x1 16->16).
+// Layer by layer the stem's output (320x320x8 split-f16 = 210 MB per 64 frames) is written and read back once: 420 MB of the
+// ~600 MB the three layers move.  Here a block owns an 8 x 16 tile of the SECOND conv's output: it stages the 35 x 67 u8 input
+// pixels the tile depends on (cp.async, 16-byte chunks, zero fill = padding; the next tile's bytes load under this tile's math),
+// computes the 17 x 33 stem outputs it needs into a shared-memory patch (stem_mma_kernel's arithmetic: contiguous-run K order,
+// exact u8 operands; positions outside the 320 x 320 stem map are stored as zeros = the second conv's padding), and then runs
+// conv_mma_kernel<3, 2, 1, 2, POST>'s MMA phase on that patch.  The stem is recomputed on the one-pixel halo (x1.1).
+constexpr int SC_TH = 8, SC_TW = 16;                          // output tile of the 3x3 s2 conv (rows x cols)
+constexpr int SC_SH = 2 * SC_TH + 1, SC_SW = 2 * SC_TW + 1;   // stem outputs the tile reads: 17 x 33
+constexpr int SC_SPIX = SC_SH * SC_SW, SC_SEG = (SC_SPIX + 15) / 16, SC_SPAD = SC_SEG * 16;   // 561 pixels = 36 MMA segments
+constexpr int SC_IR = 2 * SC_SH + 1;                          // 35 input rows
+constexpr int SC_PITCH = 208;                                 // bytes per staged input row: lead 6 + 6 * 33 + 9, rounded up to 16
+
+template <bool POST>
+__global__ void __launch_bounds__(MM_THREADS) stem_conv_kernel(const ConvParams ps, const ConvParams p, const ConvParams q,
+                                                                int tiles_x, int tiles_y, int n_tiles) {
+    constexpr int NT = 2, KSTEPS = 5, PW = SC_SW;
+    __shared__ __align__(16) uint8_t s_in[2][SC_IR * SC_PITCH];
+    __shared__ __align__(16) __half s_stem[2 * SC_SPAD * 8];     // [plane][stem pixel][8 channels]
+    constexpr int PLANE = SC_SPAD * 8;                          // halves per plane
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int per_img = tiles_x * tiles_y;
+    const int row_bytes = ps.W * 3;
+
+    // ---- weights of all three layers in registers
+    uint32_t sbh[2][2], sbl[2][2];                              // stem: B[k][n], k = 10 * ky + j, j = 1 + 3 * kx + c (stem_mma_kernel)
+    const float wscale = 4096.f / 255.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float x[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int k = 16 * ks + 8 * h + 2 * tq + i, ky = k / 10, j = k - 10 * ky;
+                x[i] = (k < 30 && j >= 1) ? __ldg(ps.w + ((ky * 3 + (j - 1) / 3) * 3 + (j - 1) % 3) * 8 + g) * wscale : 0.f;
+            }
+            split2(x[0], x[1], sbh[ks][h], sbl[ks][h]);
+        }
+    int koff[2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 16 * ks + 8 * h + 2 * tq, ky = k / 10, j = k - 10 * ky;
+            koff[ks][h] = k < 30 ? ky * SC_PITCH + j : 0;
+        }
+    const float sbias0 = __ldg(ps.bias + tq * 2), sbias1 = __ldg(ps.bias + tq * 2 + 1);
+    uint32_t bh[KSTEPS][NT][2], bl[KSTEPS][NT][2];
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) load_bfrag(p.w, 8, 16, 2 * s, 2 * s + 1, 9, 1, nt, lane, bh[s][nt], bl[s][nt]);
+    uint32_t qh[NT][2], ql[NT][2];
+    if (POST) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) load_bfrag(q.w, 16, 16, 0, 1, NT, NT, nt, lane, qh[nt], ql[nt]);
+    }
+    const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
+    const int lm = lane >> 3, lr = lane & 7;
+    const int lj = lr + 8 * (lm & 1);
+
+    // staged input of `tile`: rows 4*oy0 - 3 .. +34, bytes [12*ox0 - 16, 12*ox0 - 16 + PITCH) of each
+    auto load_in = [&](int tile, int buf) {
+        const int img = tile / per_img, tr = tile - img * per_img;
+        const int oy0 = (tr / tiles_x) * SC_TH, ox0 = (tr % tiles_x) * SC_TW;
+        const uint8_t* base = (const uint8_t*)ps.in.base + (long long)img * ps.in.img;
+        const uint32_t pb = smem_addr(s_in[buf]);
+        constexpr int CPR = SC_PITCH / 16;
+        for (int e = tid; e < SC_IR * CPR; e += MM_THREADS) {
+            const int r = e / CPR, c = e - r * CPR;
+            const int iy = 4 * oy0 - 3 + r, off = 12 * ox0 - 16 + 16 * c;
+            const bool valid = (unsigned)iy < (unsigned)ps.H && off >= 0 && off + 16 <= row_bytes;
+            cp16(pb + (uint32_t)(r * SC_PITCH + 16 * c), base + (valid ? (long long)iy * row_bytes + off : 0), valid);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int buf = 0;
+    if ((int)blockIdx.x < n_tiles) load_in(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const int img = tile / per_img, tr = tile - img * per_img;
+        const int oy0 = (tr / tiles_x) * SC_TH, ox0 = (tr % tiles_x) * SC_TW;
+        const bool more = tile + (int)gridDim.x < n_tiles;
+        if (more) load_in(tile + gridDim.x, buf ^ 1);
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                       // input bytes landed; the previous tile's MMA phase is through with s_stem
+        // ---- stem on the 17 x 33 region, 16 flat pixels per MMA segment
+        for (int seg = warp; seg < SC_SEG; seg += MM_THREADS / 32) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint8_t* pxp[2];
+            bool inside[2];
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+                const int f = min(seg * 16 + g + 8 * hr, SC_SPIX - 1);
+                const int r = f / SC_SW, c = f - r * SC_SW;
+                pxp[hr] = s_in[buf] + (2 * r) * SC_PITCH + 6 + 6 * c;            // window of this stem pixel, filter row 0, j = 0
+                const int sy = 2 * oy0 - 1 + r, sx = 2 * ox0 - 1 + c;
+                inside[hr] = (unsigned)sy < (unsigned)p.H && (unsigned)sx < (unsigned)p.W;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t a[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int hr = 0; hr < 2; ++hr) {
+                        const uint32_t raw = *reinterpret_cast<const uint16_t*>(pxp[hr] + koff[ks][h]);
+                        uint32_t v;
+                        asm("prmt.b32 %0, %1, %2, 0x4140;" : "=r"(v) : "r"(raw), "r"(0x64646464u));
+                        const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&v), k1024);
+                        a[2 * h + hr] = *reinterpret_cast<const uint32_t*>(&hv);
+                    }
+                mma16816(acc, a, sbh[ks][0], sbh[ks][1]);
+                mma16816(acc, a, sbl[ks][0], sbl[ks][1]);
+            }
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+                const int f = seg * 16 + g + 8 * hr;                             // < SC_SPAD: the tail of the last segment lands in padding
+                const float x0 = act1(fmaf(acc[2 * hr], 1.f / 4096.f, sbias0), ps.act);
+                const float x1 = act1(fmaf(acc[2 * hr + 1], 1.f / 4096.f, sbias1), ps.act);
+                uint32_t hi, lo;
+                split2(x0, x1, hi, lo);
+                *reinterpret_cast<uint32_t*>(s_stem + f * 8 + tq * 2) = inside[hr] ? hi : 0u;
+                *reinterpret_cast<uint32_t*>(s_stem + PLANE + f * 8 + tq * 2) = inside[hr] ? lo : 0u;
+            }
+        }
+        __syncthreads();
+        // ---- 3x3 s2 8 -> 16 on the stem patch (+ the fused 1x1): conv_mma_kernel<3, 2, 1, 2, POST>'s MMA phase
+        const uint32_t patch0 = smem_addr(s_stem);
+        const int cpair = tq * 2;
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+            const int oyl = 2 * warp + rt;
+            const uint32_t lane_base = patch0 + (uint32_t)((oyl * 2) * PW + lj * 2) * 16;
+#pragma unroll
+            for (int s = 0; s < KSTEPS; ++s) {
+                const int t0 = 2 * s, t1 = (2 * s + 1 < 9) ? 2 * s + 1 : 2 * s;
+                const uint32_t off0 = (uint32_t)(((t0 / 3) * PW + (t0 % 3)) * 16);
+                const uint32_t off1 = (uint32_t)(((t1 / 3) * PW + (t1 % 3)) * 16);
+                const uint32_t addr = lane_base + ((lm >> 1) ? off1 : off0);
+                uint32_t ah[4], al[4];
+                ldsm4(addr, ah);
+                ldsm4(addr + PLANE * 2, al);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma16816(acc[nt], ah, bh[s][nt][0], bh[s][nt][1]);
+                    mma16816(acc[nt], al, bh[s][nt][0], bh[s][nt][1]);
+                    mma16816(acc[nt], ah, bl[s][nt][0], bl[s][nt][1]);
+                }
+            }
+            const int oy = oy0 + oyl;
+            float v[NT][4], w[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float b0 = __ldg(p.bias + nt * 8 + cpair), b1 = __ldg(p.bias + nt * 8 + cpair + 1);
+                v[nt][0] = act1(acc[nt][0] + b0, p.act); v[nt][1] = act1(acc[nt][1] + b1, p.act);
+                v[nt][2] = act1(acc[nt][2] + b0, p.act); v[nt][3] = act1(acc[nt][3] + b1, p.act);
+            }
+            if (POST) {
+                float acc2[NT][4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc2[nt][i] = 0.f;
+                uint32_t ah[4], al[4];
+                split2(v[0][0], v[0][1], ah[0], al[0]);
+                split2(v[0][2], v[0][3], ah[1], al[1]);
+                split2(v[1][0], v[1][1], ah[2], al[2]);
+                split2(v[1][2], v[1][3], ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma16816(acc2[nt], ah, qh[nt][0], qh[nt][1]);
+                    mma16816(acc2[nt], al, qh[nt][0], qh[nt][1]);
+                    mma16816(acc2[nt], ah, ql[nt][0], ql[nt][1]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const float b0 = __ldg(q.bias + nt * 8 + cpair), b1 = __ldg(q.bias + nt * 8 + cpair + 1);
+                    w[nt][0] = act1(acc2[nt][0] + b0, q.act); w[nt][1] = act1(acc2[nt][1] + b1, q.act);
+                    w[nt][2] = act1(acc2[nt][2] + b0, q.act); w[nt][3] = act1(acc2[nt][3] + b1, q.act);
+                }
+            } else {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[nt][i] = v[nt][i];
+            }
+            const ConvParams& o = POST ? q : p;
+            if (oy >= p.Ho) continue;
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int ox = ox0 + g + 8 * hrow;
+                if (ox >= p.Wo) continue;
+                __half* oh = (__half*)o.out.base + (long long)img * o.out.img + ((long long)oy * p.Wo + ox) * o.out.C + o.out.coff;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    uint32_t hi, lo;
+                    split2(w[nt][2 * hrow], w[nt][2 * hrow + 1], hi, lo);
+                    *reinterpret_cast<uint32_t*>(oh + nt * 8 + cpair) = hi;
+                    *reinterpret_cast<uint32_t*>(oh + o.out.plane + nt * 8 + cpair) = lo;
+                }
+            }
+        }
+        // the next iteration's first barrier separates this MMA phase from the next stem phase
+    }
+}
+
 template <int KS, int STRIDE, int CH, int NT, bool POST>
 int launch_mma(lp_ctx* ctx, const ConvParams& p, const ConvParams* post, cudaStream_t st) {
     const int tiles_x = (p.Wo + MM_TW - 1) / MM_TW, tiles_y = (p.Ho + MM_TH - 1) / MM_TH;
@@ -430,5 +647,28 @@ int lp_stem_mma_try(lp_ctx* ctx, const ConvParams& p, cudaStream_t st) {
     if (p.cout == 8) stem_mma_kernel<1><<<grid, 256, 0, st>>>(p, tiles_x, tiles_y);
     else stem_mma_kernel<2><<<grid, 256, 0, st>>>(p, tiles_x, tiles_y);
     (void)ctx;
+    return 1;
+}
+
+// u8 stem (3 -> 8) + 3x3 s2 conv (8 -> 16) [+ 1x1 16 -> 16] in one kernel; the stem's output tensor is never materialised.
+// ps = the stem, p = the conv that reads ONLY the stem's output, post = its fused 1x1 or nullptr.  0: shapes not covered.
+int lp_stem_conv_try(lp_ctx* ctx, const ConvParams& ps, const ConvParams& p, const ConvParams* post, cudaStream_t st) {
+    if (ps.in.fmt != LP_FMT_U8 || ps.ksize != 3 || ps.stride != 2 || ps.cin != 3 || ps.cout != 8) return 0;
+    if (ps.in_scale_mean != 0.f || ps.in_scale_std != 1.f || ps.res.base || ps.seg_len != 0 || ps.out_cstride != 1) return 0;
+    if ((ps.W * 3) % 16 || (ps.in.img % 16) || ((uintptr_t)ps.in.base % 16) || ps.W % 4 || ps.H % 4) return 0;
+    if (p.ksize != 3 || p.stride != 2 || p.cin != 8 || p.cout != 16 || p.H != ps.Ho || p.W != ps.Wo || p.res.base || p.res_first ||
+        p.seg_len != 0 || p.out_cstride != 1 || p.out.fmt != LP_FMT_SPLIT16 || p.out.coff % 8)
+        return 0;
+    if (post && (post->cin != 16 || post->cout != 16 || post->out.fmt != LP_FMT_SPLIT16 || post->out.coff % 8 || post->res.base ||
+                 post->seg_len != 0 || post->out_cstride != 1))
+        return 0;
+    const int tiles_x = (p.Wo + SC_TW - 1) / SC_TW, tiles_y = (p.Ho + SC_TH - 1) / SC_TH;
+    const long long n_tiles = (long long)tiles_x * tiles_y * p.n_img;
+    if (n_tiles <= 0 || n_tiles > 0x7fffffff) return 0;
+    long long grid = (long long)ctx->sm_count * 4;
+    if (grid > n_tiles) grid = n_tiles;
+    const ConvParams qq = post ? *post : p;
+    if (post) stem_conv_kernel<true><<<(unsigned)grid, MM_THREADS, 0, st>>>(ps, p, qq, tiles_x, tiles_y, (int)n_tiles);
+    else stem_conv_kernel<false><<<(unsigned)grid, MM_THREADS, 0, st>>>(ps, p, qq, tiles_x, tiles_y, (int)n_tiles);
     return 1;
 }

@@ -931,6 +931,62 @@ int lp_run_plan(lp_ctx* ctx, lp_net_plan& net, const uint8_t* in, int batch, voi
                 continue;
             }
         }
+        // stem + the down-sampling conv behind it (+ its fused 1x1) in one kernel: the stem's output tensor is never materialised
+        if (ctx->use_tc && ctx->use_mma && ctx->use_c2f && op.kind == LP_OP_STEM_U8 && op.flags == 0 && oi + 1 < net.ops.size() &&
+            !(ctx->probe_net == net_id && ctx->probe_op >= (int)oi && ctx->probe_op <= (int)oi + 2)) {
+            const lp_op_desc& o1 = net.ops[oi + 1];
+            bool ok1 = o1.kind == LP_OP_CONV && o1.ksize == 3 && o1.stride == 2 && o1.in_buf == op.out_buf && o1.in_coff == op.out_coff &&
+                       o1.cin == op.cout && o1.res_buf < 0 && o1.flags == 0 && o1.out_seg_len == 0 && o1.out_cstride <= 1 &&
+                       net.bufs[o1.out_buf].fmt == LP_FMT_SPLIT16 && o1.out_buf != op.out_buf;
+            for (size_t k = 0; ok1 && k < net.ops.size(); ++k)
+                if (k != oi && k != oi + 1 && (net.ops[k].in_buf == op.out_buf || net.ops[k].res_buf == op.out_buf || net.ops[k].out_buf == op.out_buf))
+                    ok1 = false;
+            if (ok1) {
+                auto conv_params = [&](const lp_op_desc& o) {
+                    ConvParams c{};
+                    const lp_buf_desc& ib2 = net.bufs[o.in_buf];
+                    c.cin = o.cin; c.cout = o.cout; c.out_cstride = 1; c.cout_real = o.cout; c.ksize = o.ksize; c.stride = o.stride; c.act = o.act;
+                    c.n_img = batch; c.w = net.weights + o.w_off; c.bias = net.weights + o.b_off; c.in_scale_std = 1.f;
+                    c.in = make_ref(net, o.in_buf, o.in_coff, ws, 0);
+                    c.out = make_ref(net, o.out_buf, o.out_coff, ws, o.row_off);
+                    c.H = ib2.h; c.W = ib2.w;
+                    c.Ho = (c.H + 2 * (o.ksize / 2) - o.ksize) / o.stride + 1;
+                    c.Wo = (c.W + 2 * (o.ksize / 2) - o.ksize) / o.stride + 1;
+                    return c;
+                };
+                const ConvParams p1 = conv_params(o1);
+                // the 1x1 of the same width that is the only consumer of o1's output (post_candidate's rule, one op further)
+                int post_idx = -1;
+                if (oi + 2 < net.ops.size() && !(ctx->probe_net == net_id && ctx->probe_op == -2)) {
+                    const lp_op_desc& o2 = net.ops[oi + 2];
+                    bool ok2 = o2.kind == LP_OP_CONV && o2.ksize == 1 && o2.stride == 1 && o2.cin == o1.cout && o2.cout == o1.cout && o2.flags == 0 &&
+                               o2.in_buf == o1.out_buf && o2.in_coff == o1.out_coff && o2.res_buf < 0 && o2.out_seg_len == 0 && o2.out_cstride <= 1 &&
+                               o2.out_coff % 8 == 0 && net.bufs[o2.out_buf].fmt == LP_FMT_SPLIT16 && net.bufs[o2.out_buf].h == net.bufs[o1.out_buf].h &&
+                               net.bufs[o2.out_buf].w == net.bufs[o1.out_buf].w;
+                    for (size_t k = 0; ok2 && k < net.ops.size(); ++k)
+                        if (k != oi + 1 && k != oi + 2 && (net.ops[k].in_buf == o1.out_buf || net.ops[k].res_buf == o1.out_buf || net.ops[k].out_buf == o1.out_buf))
+                            ok2 = false;
+                    if (ok2) post_idx = (int)oi + 2;
+                }
+                ConvParams pq{};
+                if (post_idx >= 0) pq = conv_params(net.ops[post_idx]);
+                if (lp_stem_conv_try(ctx, p, p1, post_idx >= 0 ? &pq : nullptr, st)) {
+                    LP_LAUNCH_OK(ctx);
+                    net.last_path[oi] = 4;
+                    const int n_abs = post_idx >= 0 ? 2 : 1;
+                    for (int j = 1; j <= n_abs; ++j) {
+                        net.last_path[oi + j] = 3;
+                        if (probe_all && (int)(oi + j) < LP_PROBE_RING) {
+                            LP_CUDA(cudaEventRecord(ctx->probe_ev[2 * (oi + j)], st));
+                            LP_CUDA(cudaEventRecord(ctx->probe_ev[2 * (oi + j) + 1], st));
+                            if (ctx->probe_n < (int)(oi + j) + 1) ctx->probe_n = (int)(oi + j) + 1;
+                        }
+                    }
+                    oi += n_abs;
+                    continue;
+                }
+            }
+        }
         if (ctx->use_tc && ctx->use_mma && op.kind == LP_OP_STEM_U8 && op.flags == 0 && lp_stem_mma_try(ctx, p, st)) {
             LP_LAUNCH_OK(ctx);
             net.last_path[oi] = 4;
