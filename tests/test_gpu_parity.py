@@ -371,6 +371,25 @@ def test_fused_c2f_body_equals_layer_by_layer(lp, v1_paths, v2_paths, monkeypatc
     assert d[:, :4].max() < BOX_TOL and d[:, 4:].max() < SCORE_TOL
 
 
+@pytest.mark.parametrize("which", ["v1", "v2"])
+def test_tma_patch_loads_equal_cp_async_loads(lp, v1_paths, v2_paths, monkeypatch, which):
+    """conv_tc.cu moves the activation patches by TMA tensor copies (chunk-major boxes for the 3x3 layers, SWIZZLE_128B pixel rows
+    for the 1x1 layers with cin % 64 == 0) or, with LP_TC_TMA=0, by cp.async from five loader warps.  Only the transport and the
+    shared-memory layout differ: K order and accumulation order are the same, so out0 must be IDENTICAL bit for bit -- including
+    the zero fill of the halo, the partial last tile of a 1x1 layer (batch 3 of a max_batch 4 plan) and frames of different
+    content in one batch."""
+    param, binp = (v1_paths if which == "v1" else (v2_paths[0], None))
+    x = np.random.default_rng(33).integers(0, 256, (3, 640, 640, 3), dtype=np.uint8)
+    a = lp.B200Detector(param, binp, max_batch=4, seed=2).forward(x)
+    monkeypatch.setenv("LP_TC_TMA", "0")
+    b = lp.B200Detector(param, binp, max_batch=4, seed=2).forward(x)
+    monkeypatch.setenv("LP_TC_TMA", "3")
+    monkeypatch.setenv("LP_TC_SW128", "0")
+    c = lp.B200Detector(param, binp, max_batch=4, seed=2).forward(x)
+    monkeypatch.delenv("LP_TC_TMA"); monkeypatch.delenv("LP_TC_SW128")
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
 def test_classifier_default_init_state_dict(lp):
     """the reference's own construction: torchvision random init + fc swap, default BatchNorm"""
     import torch.nn as nn

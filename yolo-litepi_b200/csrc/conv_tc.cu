@@ -937,7 +937,7 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     }
     // Patch loads by TMA tensor copies (3x3 stride 1 and 1x1; the stride-2 phase split keeps cp.async).  LP_TC_TMA: 0 off, 1 3x3 only,
     // 2 1x1 only, 3 both (default).
-    { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_TMA"); f = e ? atoi(e) : 3; }
+    { const int f = ctx->tc_tma;
       p.use_tma = ((op.ksize == 3 && op.stride == 1 && (f & 1)) || (op.ksize == 1 && (f & 2))) ? 1 : 0; }
     if (p.use_tma && (p.dbg_flags & 1)) p.use_tma = 0;
     // chunk stride: == 1 (mod 8) slots keeps the cp.async writes conflict-free; a tensor copy needs a 128-byte aligned destination
@@ -1017,8 +1017,7 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     if (!ok) return 0;
     p.fills_per_tile = p.resident ? 0 : p.n_kb / p.w_stages;
     // swizzled A tiles: 1x1 layers whose K splits into 64-channel blocks (same bytes per patch stage as the chunk layout)
-    { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_SW128"); f = e ? atoi(e) : 1; }
-      p.a_sw128 = (f && p.use_tma && op.ksize == 1 && op.cin % 64 == 0 && p.kb_ch == 64) ? 1 : 0; }
+    p.a_sw128 = (ctx->tc_sw128 && p.use_tma && op.ksize == 1 && op.cin % 64 == 0 && p.kb_ch == 64) ? 1 : 0;
     // Two issuing warps (split_mma) need a third accumulator piece per stage.  Measured (profiles/r2_notes.md): with
     // cout <= 32 (four accumulator stages of 3 * cout columns still fit the 512 TMEM columns) the 3x3 layers gain 8-10 %;
     // at cout = 64 only two stages fit and the MMA warps wait for the epilogue (conv_48: 110 -> 122 us), so those layers
