@@ -725,31 +725,33 @@ __global__ void __launch_bounds__(256) sppf3_kernel(ConvParams p, int slice_stri
     }
     __syncthreads();
     float* tmp = s_map + 2 * hw * 8;                    // row maxima (the 5x5 window is separable: 5 + 5 taps instead of 25)
+    // thread = pixel, all 8 channels of the chunk in two float4 (one element per thread cost ~60 instructions of index
+    // arithmetic and bounds tests per tap pass; per pixel they are paid once for eight channels)
+    auto max8 = [](float4& m0, float4& m1, const float* q) {
+        const float4 v0 = *reinterpret_cast<const float4*>(q), v1 = *reinterpret_cast<const float4*>(q + 4);
+        m0.x = fmaxf(m0.x, v0.x); m0.y = fmaxf(m0.y, v0.y); m0.z = fmaxf(m0.z, v0.z); m0.w = fmaxf(m0.w, v0.w);
+        m1.x = fmaxf(m1.x, v1.x); m1.y = fmaxf(m1.y, v1.y); m1.z = fmaxf(m1.z, v1.z); m1.w = fmaxf(m1.w, v1.w);
+    };
     for (int pass = 0; pass < 3; ++pass) {
-        for (int e = threadIdx.x; e < hw * 8; e += blockDim.x) {
-            const int px = e >> 3, k = e & 7;
+        for (int px = threadIdx.x; px < hw; px += blockDim.x) {
             const int oy = px / p.W, ox = px - oy * p.W;
-            float m = -INFINITY;
-            for (int kx = -2; kx <= 2; ++kx) {
-                const int ix = ox + kx;
-                if (ix >= 0 && ix < p.W) m = fmaxf(m, a[(oy * p.W + ix) * 8 + k]);
-            }
-            tmp[e] = m;
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < hw * 8; e += blockDim.x) {
-            const int px = e >> 3, k = e & 7;
-            const int oy = px / p.W, ox = px - oy * p.W;
-            float m = -INFINITY;
-            for (int ky = -2; ky <= 2; ++ky) {
-                const int iy = oy + ky;
-                if (iy >= 0 && iy < p.H) m = fmaxf(m, tmp[(iy * p.W + ox) * 8 + k]);
-            }
-            b[e] = m;
+            const int x_lo = max(ox - 2, 0), x_hi = min(ox + 2, p.W - 1);
+            float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
+            for (int ix = x_lo; ix <= x_hi; ++ix) max8(m0, m1, a + (oy * p.W + ix) * 8);
+            *reinterpret_cast<float4*>(tmp + px * 8) = m0;
+            *reinterpret_cast<float4*>(tmp + px * 8 + 4) = m1;
         }
         __syncthreads();
         const long long out0 = (long long)img * p.out.img + p.out.coff + (long long)pass * slice_stride + ch * 8;
-        for (int px = threadIdx.x; px < hw; px += blockDim.x) st8(p.out, out0 + (long long)px * p.out.C, b + px * 8);
+        for (int px = threadIdx.x; px < hw; px += blockDim.x) {
+            const int oy = px / p.W, ox = px - oy * p.W;
+            const int y_lo = max(oy - 2, 0), y_hi = min(oy + 2, p.H - 1);
+            float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
+            for (int iy = y_lo; iy <= y_hi; ++iy) max8(m0, m1, tmp + (iy * p.W + ox) * 8);
+            *reinterpret_cast<float4*>(b + px * 8) = m0;
+            *reinterpret_cast<float4*>(b + px * 8 + 4) = m1;
+            st8(p.out, out0 + (long long)px * p.out.C, b + px * 8);      // this thread's own pixel: no barrier needed before the store
+        }
         float* t = a; a = b; b = t;
         __syncthreads();
     }
