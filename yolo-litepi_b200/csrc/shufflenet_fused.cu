@@ -190,17 +190,22 @@ __device__ __forceinline__ void pw_layer_mma(const float* __restrict__ in, int i
     }
 }
 
-// Tensor-core pointwise layer of the TAIL pass: few rows (the CTA's stacked ROIs x 1..16 pixels) and long K, so a weight
-// chunk holds only 2-6 output tiles.  To keep all 16 warps busy the K steps of a tile are split over KSPLIT warps and the
-// partial 16x8 tiles are summed through shared memory in a fixed order (red[tile][slice][128]).  KSPLIT is derived from
-// the capacity of the pass (m_cap row tiles), never from how many ROIs are stacked this time.
-__device__ __forceinline__ void pw_layer_mma_ks(const float* __restrict__ in, int in_C, float* __restrict__ out, int out_C, int dst_cs,
-                                                int rows, int m_cap, int cin, int cout, const float* __restrict__ bias, int relu,
-                                                __half* __restrict__ astage, float* __restrict__ red, const float* __restrict__ wbuf,
-                                                int slot_floats, uint64_t* full, uint64_t* empty, uint32_t& chunk_ctr) {
+// Tensor-core pointwise layer of the TAIL pass: few rows (the CTA's stacked ROIs x 1..16 pixels = one to three 16-row tiles) and
+// long K, 73 % of the network's weight bytes.  No shared-memory weight stages: the fp16 hi|lo weights are stored in MMA-fragment
+// order ([n_tile][k_step][lane] x 16 bytes, plan.py), every warp owns whole 8-channel output tiles and streams their fragments
+// from L2 straight into registers with coalesced 512-byte loads, four K-steps in flight.  One warp sums a tile's whole K in a fixed
+// order, so a ROI's result does not depend on how many ROIs are stacked.  (A first version chunked the weights along N through the
+// two 44 KB ring stages -- 43 chunks of 3 tiles for conv5, each with two block barriers and a K-slice reduction -- and was
+// slower than the fp32 path.)  MEASURED (tools/cls_steps.py, tools/cls_tail.py): this path and the fp32 path take the same time
+// (stage-4 layers 16.8 k vs 18.4 k cycles, conv5 112 k vs 103 k): the tail is bound by its weight stream -- 148 SMs each pulling the
+// same 3.8 MB from L2, ~30 KB/us per SM = 4.4 TB/s aggregate -- not by the arithmetic, so it stays OFF by default (LP_CLS_TAIL_MMA=1
+// enables it; tail group <= 2, its activation staging needs the room of the third ROI).
+__device__ __forceinline__ void pw_layer_mma_direct(const float* __restrict__ in, int in_C, float* __restrict__ out, int out_C, int dst_cs,
+                                                    int rows, int cin, int cout, const float* __restrict__ bias, int relu,
+                                                    __half* __restrict__ astage, const uint4* __restrict__ wfrag) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rows_p = (rows + 15) & ~15, cin_p = (cin + 15) & ~15, cout_p = (cout + 7) & ~7;
-    const int LA = cin_p + 8, L = w16_row_halves(cin);
+    const int LA = cin_p + 8;
     __half* Ah = astage;
     __half* Al = astage + rows_p * LA;
     for (int e = tid; e < rows_p * (cin_p >> 1); e += FUSED_THREADS) {
@@ -216,77 +221,58 @@ __device__ __forceinline__ void pw_layer_mma_ks(const float* __restrict__ in, in
         *reinterpret_cast<__half2*>(Al + r * LA + c) = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
     }
     CSYNC();
-    const int m_tiles = rows_p >> 4, ksteps = cin_p >> 4;
-    const int NN = chunk_couts(cin, cout, slot_floats);
-    constexpr int NW = FUSED_THREADS / 32;
-    for (int n0 = 0; n0 < cout_p; n0 += NN, ++chunk_ctr) {
-        const int nn = min(NN, cout_p - n0);
-        const uint32_t slot = chunk_ctr & 1;
-        f_mbar_wait(&full[slot], (chunk_ctr >> 1) & 1);
-        const __half* Wc = reinterpret_cast<const __half*>(wbuf + slot * slot_floats);      // [nn][2][L]
-        const int n_tiles = nn >> 3;
-        int ksplit = NW / (m_cap * n_tiles);
-        ksplit = ksplit < 1 ? 1 : (ksplit > ksteps ? ksteps : ksplit);
-        if (ksplit > 8) ksplit = 8;
-        const int items = m_tiles * n_tiles * ksplit;
-        for (int item = warp; item < items; item += NW) {
-            const int tile = item / ksplit, slice = item - tile * ksplit;
-            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-            const int ks0 = (slice * ksteps) / ksplit, ks1 = ((slice + 1) * ksteps) / ksplit;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const __half* arow_h = Ah + (mt * 16 + (lane & 15)) * LA + (lane >> 4) * 8;
-            const __half* arow_l = arow_h + rows_p * LA;
-            const __half* brow = Wc + (size_t)(nt * 8 + (lane >> 2)) * 2 * L + (lane & 3) * 2;
-#pragma unroll 2
-            for (int ks = ks0; ks < ks1; ++ks) {
-                uint32_t ah[4], al[4];
-                ldmatrix_x4(ah, arow_h + ks * 16);
-                ldmatrix_x4(al, arow_l + ks * 16);
-                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(brow + ks * 16);
-                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(brow + ks * 16 + 8);
-                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(brow + L + ks * 16);
-                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(brow + L + ks * 16 + 8);
-                mma_f16(acc, ah, bh0, bh1);
-                mma_f16(acc, al, bh0, bh1);
-                mma_f16(acc, ah, bl0, bl1);
+    const int m_tiles = rows_p >> 4, ksteps = cin_p >> 4, n_tiles = cout_p >> 3;
+    constexpr int NW = FUSED_THREADS / 32, MT = 3, PF = 4;        // row tiles per weight pass, K-steps of weights in flight
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int mt0 = 0; mt0 < m_tiles; mt0 += MT) {
+        for (int nt = warp; nt < n_tiles; nt += NW) {
+            float acc[MT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[m][i] = 0.f;
+            const uint4* wp = wfrag + (size_t)nt * ksteps * 32 + lane;
+            const __half* arow_h = Ah + (mt0 * 16 + (lane & 15)) * LA + (lane >> 4) * 8;
+            uint4 cur[PF];
+#pragma unroll
+            for (int i = 0; i < PF; ++i) cur[i] = i < ksteps ? __ldg(wp + i * 32) : zero4;
+            for (int ks0 = 0; ks0 < ksteps; ks0 += PF) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    if (ks0 + i < ksteps) {
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            if (mt0 + m < m_tiles) {
+                                uint32_t ah[4], al[4];
+                                ldmatrix_x4(ah, arow_h + m * 16 * LA + (ks0 + i) * 16);
+                                ldmatrix_x4(al, arow_h + m * 16 * LA + rows_p * LA + (ks0 + i) * 16);
+                                mma_f16(acc[m], ah, cur[i].x, cur[i].y);
+                                mma_f16(acc[m], al, cur[i].x, cur[i].y);
+                                mma_f16(acc[m], ah, cur[i].z, cur[i].w);
+                            }
+                        }
+                    }
+                    // the register set of this K-step is free again: fetch the step PF further on into it
+                    if (ks0 + PF + i < ksteps) cur[i] = __ldg(wp + (ks0 + PF + i) * 32);
+                }
             }
-            if (ksplit == 1) {                        // whole K in this warp: epilogue straight from the fragments
-                const int c = n0 + nt * 8 + (lane & 3) * 2;
+            const int c = nt * 8 + (lane & 3) * 2;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                if (mt0 + m >= m_tiles) continue;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int r = mt * 16 + (lane >> 2) + 8 * h;
+                    const int r = (mt0 + m) * 16 + (lane >> 2) + 8 * h;
                     if (r >= rows) continue;
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
                         if (c + j < cout) {
-                            const float v = acc[2 * h + j] + __ldg(bias + c + j);
+                            const float v = acc[m][2 * h + j] + __ldg(bias + c + j);
                             out[(size_t)r * out_C + (c + j) * dst_cs] = relu ? fmaxf(v, 0.f) : v;
                         }
                 }
-            } else {
-                *reinterpret_cast<float4*>(red + ((size_t)(tile * ksplit + slice) * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
             }
         }
-        if (ksplit == 1) {
-            f_mbar_arrive(&empty[slot]);
-            continue;
-        }
-        CSYNC();
-        // fixed-order sum of the K slices, then bias / ReLU / shuffle store; element e of a tile belongs to lane e/4
-        for (int t = tid; t < m_tiles * n_tiles * 128; t += FUSED_THREADS) {
-            const int tile = t >> 7, e = t & 127, ln = e >> 2, q = e & 3;
-            const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-            float v = 0.f;
-            for (int sl = 0; sl < ksplit; ++sl) v += red[((size_t)(tile * ksplit + sl) * 32 + ln) * 4 + q];
-            const int r = mt * 16 + (ln >> 2) + 8 * (q >> 1);
-            const int c = n0 + nt * 8 + (ln & 3) * 2 + (q & 1);
-            if (r < rows && c < cout) {
-                v += __ldg(bias + c);
-                out[(size_t)r * out_C + c * dst_cs] = relu ? fmaxf(v, 0.f) : v;
-            }
-        }
-        f_mbar_arrive(&empty[slot]);              // 512 arrivals free the stage for the producer
-        CSYNC();                                  // red is reused by the next chunk
     }
 }
 
@@ -478,6 +464,7 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                     for (int si = s_begin; si < s_end; ++si) {
                         const FStep& st = s_steps[si];
                         if (st.op != FS_PW) continue;
+                        if (kind == 2 && st.w16_off > 0) continue;       // tail tensor-core layers read their weights straight from L2
                         if (kind != 0 && st.w16_off > 0) {
                             // tensor-core layer: chunks of output channels, rows of 2 planes x L halves (4*L bytes)
                             const int NN = chunk_couts(st.cin, st.cout, slot_floats), cout_p8 = (st.cout + 7) & ~7;
@@ -671,9 +658,8 @@ shufflenet_fused_kernel(const uint8_t* __restrict__ in, int n_rois_cap, const in
                         break;
                     }
                     if (kind == 2 && st.w16_off > 0) {
-                        pw_layer_mma_ks(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, (GT * st.H * st.W + 15) >> 4, st.cin, st.cout,
-                                        W + st.b_off, st.relu, reinterpret_cast<__half*>(sm + tail_astage_off), sm + tail_red_off,
-                                        wst, wst_floats, s_full, s_empty, chunk_ctr);
+                        pw_layer_mma_direct(ip, st.src_C, op, st.dst_C, st.dst_cs, rows, st.cin, st.cout, W + st.b_off, st.relu,
+                                            reinterpret_cast<__half*>(sm + tail_astage_off), W16 + (st.w16_off - 1));
                         break;
                     }
                     // RT = min(8, rows) rows per thread; K split over the largest power of two <= 8 that keeps

@@ -557,6 +557,7 @@ def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, 
     h16: List[np.ndarray] = []
     nh = [0]
     last16 = [0]
+    frag_mode = [False]     # True while the tail is emitted with tail_mma: fp16 weights in MMA-fragment order (read straight from L2)
 
     def pw_w(conv, bn):
         w, b = _fold_bn(sd[conv + ".weight"], sd, bn)                # [cout, cin, 1, 1]
@@ -566,7 +567,23 @@ def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, 
         bp = np.zeros(cp, np.float32); bp[:cout] = b
         # tensor-core copy: [cout_p8][hi|lo][L] fp16, L = cin_p16 + pad with L == 4 (mod 32) (csrc w16_row_halves)
         last16[0] = 0
-        if True:                        # every pointwise layer gets an fp16 copy; which ones use it is decided per pass
+        if frag_mode[0]:
+            # [n_tile][k_step][lane][bh0, bh1, bl0, bl1]: lane (g, t) holds B[k = 16*ks + 2t (+1, +8, +9)][n = 8*nt + g] of the hi and
+            # of the lo plane -- the operand registers of mma.m16n8k16, so a warp loads one coalesced 512-byte line per (n_tile, k_step)
+            cin_p = (cin + 15) // 16 * 16
+            cout_p8 = (cout + 7) // 8 * 8
+            w2 = np.zeros((cout_p8, cin_p), np.float32); w2[:cout, :cin] = w.reshape(cout, cin)
+            hi = w2.astype(np.float16)
+            lo = (w2 - hi.astype(np.float32)).astype(np.float16)
+            nt_i, ks_i, ln_i = np.meshgrid(np.arange(cout_p8 // 8), np.arange(cin_p // 16), np.arange(32), indexing="ij")
+            n_i = nt_i * 8 + ln_i // 4
+            k_i = ks_i * 16 + 2 * (ln_i % 4)
+            blk = np.stack([hi[n_i, k_i], hi[n_i, k_i + 1], hi[n_i, k_i + 8], hi[n_i, k_i + 9],
+                            lo[n_i, k_i], lo[n_i, k_i + 1], lo[n_i, k_i + 8], lo[n_i, k_i + 9]], axis=-1)
+            assert nh[0] % 8 == 0
+            last16[0] = nh[0] // 8 + 1
+            h16.append(np.ascontiguousarray(blk, np.float16).ravel()); nh[0] += blk.size
+        elif True:                      # every pointwise layer gets an fp16 copy; which ones use it is decided per pass
             cin_p = (cin + 15) // 16 * 16
             L = cin_p + ((4 - cin_p) % 32)
             w2 = w.reshape(cout, cin).astype(np.float32)
@@ -686,6 +703,7 @@ def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, 
     t_a = t_t2 + GT * (hw // 2) ** 2 * bf4
     tail_floats = t_a + GT * (hw // 2) ** 2 * 2 * bf4
     step(FS_LOAD, 0, t_in, dst_C=2 * widths[1], cout=2 * widths[1], H=hw, W=hw, roi_stride=park)
+    frag_mode[0] = bool(tail_mma)
     # unit 0 reads IN and writes A; the basic units ping-pong between A and the (now dead) IN region
     X, OUT, hw = emit_units(4, bf4, t_in, t_a, t_t1, t_t2, hw, False)
     wo, bo, ci, co = pw_w("conv5.0", "conv5.1")
@@ -714,9 +732,10 @@ def build_fused_classifier(state_dict: dict, group: int = 1, in_size: int = 64, 
         ncg = (st[9] + 3) // 4
         rt = 4 if (cap == 12 and 3 * ncg <= 512) else (8 if cap >= 8 else 4 if cap >= 4 else 2 if cap >= 2 else 1)
         assert -(-cap // rt) * ncg <= 512, f"fused classifier: step {k} needs {-(-cap // rt) * ncg} tiles"
-    # tail: rows = the stacked ROIs.  tail_mma: its pointwise layers on the tensor cores with K split over the warps
-    # (csrc pw_layer_mma_ks).  Measured SLOWER than the fp32 path (333 ROIs: 947 vs 797 us at tail_group 2; the fp16
-    # staging and the partial-sum buffer shrink the weight stages, and group 3 no longer fits), hence off by default.
+    # tail: rows = the stacked ROIs.  tail_mma: its pointwise layers on the tensor cores (csrc pw_layer_mma_direct): every warp owns
+    # whole output tiles and streams their fragment-ordered weights straight from L2 into registers -- no shared-memory weight
+    # stages, no K split, no partial sums (the first tensor-core tail chunked the weights along N through the 2 x 44 KB ring:
+    # 43 chunks of 3 output tiles for conv5, each with two barriers and a reduction, and measured slower than the fp32 path).
     tail_astage = 0
     for st in steps[n_front + n_mid:]:
         if st[0] == FS_PW and st[17] > 0:
