@@ -861,6 +861,22 @@ unsigned magic_u32(int n) { return (unsigned)((0x100000000ull + (unsigned)n - 1)
 static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st,
                          int n0, int nb, size_t wtc_off);
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table: the library must load (and export its symbols) on a
+// machine without libcuda.so.1 -- the CPU-only build / test box -- so it carries no link-time dependency on the driver.
+typedef CUresult (*lp_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static lp_encode_tiled_fn lp_encode_tiled() {
+    static lp_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<lp_encode_tiled_fn>(p);
+    }
+    return fn;
+}
+
 // returns 1 if the op ran on the tensor cores, 0 if it is not eligible, <0 on error
 int lp_conv_tc_try(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, int batch, uint8_t* ws, cudaStream_t st) {
     const lp_buf_desc& ib = net.bufs[op.in_buf];
@@ -1057,18 +1073,20 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     if (p.use_tma) {
         // the tensor map is a view of the whole input buffer; the lo plane is image max_batch + i (make_ref: plane = max_batch images)
         CUresult cr;
+        const lp_encode_tiled_fn encode = lp_encode_tiled();
+        LP_CHECK(encode != nullptr, "conv_tc: the driver does not export cuTensorMapEncodeTiled");
         if (op.ksize == 1) {
             const cuuint64_t dims[2] = {(cuuint64_t)ib.c, (cuuint64_t)2 * net.max_batch * ib.h * ib.w};
             const cuuint64_t strides[1] = {(cuuint64_t)ib.c * 2};
             const cuuint32_t box[2] = {p.a_sw128 ? 64u : 8u, (cuuint32_t)TILE_M}, es[2] = {1, 1};
-            cr = cuTensorMapEncodeTiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.in), dims, strides, box, es,
+            cr = encode(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.in), dims, strides, box, es,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, p.a_sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
             const cuuint64_t dims[4] = {(cuuint64_t)ib.c, (cuuint64_t)ib.w, (cuuint64_t)ib.h, (cuuint64_t)2 * net.max_batch};
             const cuuint64_t strides[3] = {(cuuint64_t)ib.c * 2, (cuuint64_t)ib.w * ib.c * 2, (cuuint64_t)ib.image_bytes};
             const cuuint32_t box[4] = {8, (cuuint32_t)p.pitch, (cuuint32_t)(TCT_H + 2), 1}, es[4] = {1, 1, 1, 1};
-            cr = cuTensorMapEncodeTiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.in), dims, strides, box, es,
+            cr = encode(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.in), dims, strides, box, es,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
