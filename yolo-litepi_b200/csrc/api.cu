@@ -37,7 +37,7 @@ extern "C" int lp_create(lp_ctx** out, int device) {
     { const char* e = getenv("LP_NO_PDL"); c->use_pdl = (e && e[0] == '1') ? 0 : 1; }
     { const char* e = getenv("LP_NO_MMA"); c->use_mma = (e && e[0] == '1') ? 0 : 1; }
     { const char* e = getenv("LP_NO_C2F"); c->use_c2f = (e && e[0] == '1') ? 0 : 1; }
-    { const char* e = getenv("LP_TC_TMA"); c->tc_tma = e ? atoi(e) : 3; }
+    { const char* e = getenv("LP_TC_TMA"); c->tc_tma = e ? atoi(e) : 7; }
     { const char* e = getenv("LP_TC_SW128"); c->tc_sw128 = e ? atoi(e) : 1; }
     c->sm_count = prop.multiProcessorCount;
     *out = c;

@@ -73,7 +73,7 @@ struct lp_ctx {
     int use_fused = 1;
     int use_mma = 1;                 // warp-level MMA kernels for the small-channel layers (env LP_NO_MMA=1: fp32-FMA kernels instead)
     int use_c2f = 1;                 // fused C2f-body kernel for c = 8 / 16 (env LP_NO_C2F=1: layer by layer)
-    int tc_tma = 3;                  // conv_tc patch loads by TMA tensor copies: bit 0 = 3x3 stride 1, bit 1 = 1x1 (env LP_TC_TMA, read by lp_create)
+    int tc_tma = 7;                  // conv_tc patch loads by TMA tensor copies: bit 0 = 3x3 stride 1, bit 1 = 1x1, bit 2 = 3x3 stride 2 (env LP_TC_TMA, read by lp_create)
     int tc_sw128 = 1;                // SWIZZLE_128B A tiles for the 1x1 layers with cin % 64 == 0 (env LP_TC_SW128)
     int use_pdl = 1;                 // programmatic dependent launch between tensor-core conv kernels (env LP_NO_PDL=1 disables)
     int roi_mode = 0;                // 0: e2e.py ROI rules + Pillow resize; 1: e2e_optimize.py rules + cv2 INTER_LINEAR

@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (it >= p.patch_stages) mbar_wait(&patch_empty[ps], ps_phase ^ 1);
                     const TileCoord tc = tile_coord(p, tile);
                     const uint32_t dst0 = smem_u32(patch0 + (size_t)ps * patch_bytes);
-                    mbar_expect_tx(&patch_full[ps], 2u * (uint32_t)n_chunks * (uint32_t)p.tma_box_bytes);
+                    mbar_expect_tx(&patch_full[ps], (p.stride == 2 ? 8u : 2u) * (uint32_t)n_chunks * (uint32_t)p.tma_box_bytes);
                     if (SW) {
                         const long long lo_pix = (long long)p.max_batch * hw_in;
                         const int n_blk = n_chunks >> 3;                       // 64-channel blocks
@@ -509,11 +509,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             for (int ch = 0; ch < n_chunks; ++ch)
                                 tma_load_2d(dst0 + (uint32_t)pl * plane_bytes + (uint32_t)ch * chunk_bytes, tmap, c_base + 8 * ch,
                                             (int)(tc.pix0 + pl * lo_pix), &patch_full[ps]);
-                    } else {
+                    } else if (p.stride == 1) {
                         for (int pl = 0; pl < 2; ++pl)
                             for (int ch = 0; ch < n_chunks; ++ch)
                                 tma_load_4d(dst0 + (uint32_t)pl * plane_bytes + (uint32_t)ch * chunk_bytes, tmap, c_base + 8 * ch,
                                             tc.ox0 - 1, tc.oy0 - 1, pl * p.max_batch + tc.img, &patch_full[ps]);
+                    } else {
+                        // stride 2: phase (row parity, column parity) = the window's pixels (2*sr + pr, 2*sc + pc), sampled by the map's element strides
+                        const uint32_t phase_bytes = (uint32_t)p.phase_slots * 16;
+                        for (int pl = 0; pl < 2; ++pl)
+                            for (int ch = 0; ch < n_chunks; ++ch)
+                                for (int ph = 0; ph < 4; ++ph)
+                                    tma_load_4d(dst0 + (uint32_t)pl * plane_bytes + (uint32_t)ch * chunk_bytes + (uint32_t)ph * phase_bytes, tmap,
+                                                c_base + 8 * ch, 2 * tc.ox0 - 1 + (ph & 1), 2 * tc.oy0 - 1 + (ph >> 1),
+                                                pl * p.max_batch + tc.img, &patch_full[ps]);
                     }
                     if (++ps == (uint32_t)p.patch_stages) { ps = 0; ps_phase ^= 1; }
                 }
@@ -944,22 +953,27 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     p.Ho = (ib.h + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1;
     p.Wo = (ib.w + 2 * (op.ksize / 2) - op.ksize) / op.stride + 1;
     const int taps = op.ksize * op.ksize;
+    // Patch loads by TMA tensor copies.  ctx->tc_tma (env LP_TC_TMA): bit 0 = 3x3 stride 1, bit 1 = 1x1, bit 2 = 3x3 stride 2; default all.
+    { const int f = ctx->tc_tma;
+      p.use_tma = ((op.ksize == 3 && op.stride == 1 && (f & 1)) || (op.ksize == 1 && (f & 2)) || (op.ksize == 3 && op.stride == 2 && (f & 4))) ? 1 : 0; }
+    if (p.use_tma && (p.dbg_flags & 1)) p.use_tma = 0;
     if (op.ksize == 1) { p.slots = TILE_M; p.pitch = 8; }
     else if (op.stride == 1) { p.pitch = TCT_W + 2; p.slots = (TCT_H + 2) * p.pitch; }
-    else { p.pitch = TCT_W + 1; p.phase_slots = (TCT_H + 1) * p.pitch; p.slots = 4 * p.phase_slots; }
+    else {
+        // stride 2: the four (row, column) parity phases of the 33 x 17 patch, 17 x 9 slots each; a tensor copy (one per phase) needs a
+        // 128-byte aligned destination, so with TMA a phase occupies 160 slots
+        p.pitch = TCT_W + 1;
+        p.phase_slots = p.use_tma ? ((TCT_H + 1) * p.pitch + 7) / 8 * 8 : (TCT_H + 1) * p.pitch;
+        p.slots = 4 * p.phase_slots;
+    }
     for (int t = 0; t < taps; ++t) {
         const int ky = t / 3, kx = t % 3;
         p.tap_off[t] = op.ksize == 1 ? 0 : op.stride == 1 ? ky * p.pitch + kx : ((ky & 1) * 2 + (kx & 1)) * p.phase_slots + (ky >> 1) * p.pitch + (kx >> 1);
     }
-    // Patch loads by TMA tensor copies (3x3 stride 1 and 1x1; the stride-2 phase split keeps cp.async).  LP_TC_TMA: 0 off, 1 3x3 only,
-    // 2 1x1 only, 3 both (default).
-    { const int f = ctx->tc_tma;
-      p.use_tma = ((op.ksize == 3 && op.stride == 1 && (f & 1)) || (op.ksize == 1 && (f & 2))) ? 1 : 0; }
-    if (p.use_tma && (p.dbg_flags & 1)) p.use_tma = 0;
     // chunk stride: == 1 (mod 8) slots keeps the cp.async writes conflict-free; a tensor copy needs a 128-byte aligned destination
     p.slots_p = p.use_tma ? (p.slots + 7) / 8 * 8 : p.slots + ((9 - (p.slots & 7)) & 7);
     p.plane_bytes = (op.cin / 8) * p.slots_p * 16;
-    p.tma_box_bytes = p.slots * 16;
+    p.tma_box_bytes = (op.ksize == 3 && op.stride == 2) ? (TCT_H + 1) * p.pitch * 16 : p.slots * 16;     // stride 2: one box per phase
     p.max_batch = net.max_batch;
     p.magic_chunks = magic_u32(op.cin / 8);
     p.magic_pitch = magic_u32(p.pitch);
@@ -1085,7 +1099,10 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
         } else {
             const cuuint64_t dims[4] = {(cuuint64_t)ib.c, (cuuint64_t)ib.w, (cuuint64_t)ib.h, (cuuint64_t)2 * net.max_batch};
             const cuuint64_t strides[3] = {(cuuint64_t)ib.c * 2, (cuuint64_t)ib.w * ib.c * 2, (cuuint64_t)ib.image_bytes};
-            const cuuint32_t box[4] = {8, (cuuint32_t)p.pitch, (cuuint32_t)(TCT_H + 2), 1}, es[4] = {1, 1, 1, 1};
+            // stride 1: the 18 x 10 halo patch; stride 2: every other pixel of a 33 x 17 window = one 17 x 9 parity phase per copy
+            const cuuint32_t s2 = op.stride == 2 ? 1u : 0u;
+            const cuuint32_t box[4] = {8, s2 ? 2u * TCT_W + 1u : (cuuint32_t)p.pitch, s2 ? 2u * TCT_H + 1u : (cuuint32_t)(TCT_H + 2), 1};
+            const cuuint32_t es[4] = {1, s2 ? 2u : 1u, s2 ? 2u : 1u, 1};
             cr = encode(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.in), dims, strides, box, es,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
