@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(MM_THREADS) stem_conv_kernel(const ConvParams 
 #pragma unroll
             for (int hr = 0; hr < 2; ++hr) {
                 const int f = seg * 16 + g + 8 * hr;                             // < SC_SPAD: the tail of the last segment lands in padding
-                const float x0 = act1(fmaf(acc[2 * hr], 1.f / 4096.f, sbias0), ps.act);
-                const float x1 = act1(fmaf(acc[2 * hr + 1], 1.f / 4096.f, sbias1), ps.act);
+                const float x0 = lp_silu(fmaf(acc[2 * hr], 1.f / 4096.f, sbias0));
+                const float x1 = lp_silu(fmaf(acc[2 * hr + 1], 1.f / 4096.f, sbias1));
                 uint32_t hi, lo;
                 split2(x0, x1, hi, lo);
                 *reinterpret_cast<uint32_t*>(s_stem + f * 8 + tq * 2) = inside[hr] ? hi : 0u;
@@ -545,8 +545,8 @@ __global__ void __launch_bounds__(MM_THREADS) stem_conv_kernel(const ConvParams 
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const float b0 = __ldg(p.bias + nt * 8 + cpair), b1 = __ldg(p.bias + nt * 8 + cpair + 1);
-                v[nt][0] = act1(acc[nt][0] + b0, p.act); v[nt][1] = act1(acc[nt][1] + b1, p.act);
-                v[nt][2] = act1(acc[nt][2] + b0, p.act); v[nt][3] = act1(acc[nt][3] + b1, p.act);
+                v[nt][0] = lp_silu(acc[nt][0] + b0); v[nt][1] = lp_silu(acc[nt][1] + b1);
+                v[nt][2] = lp_silu(acc[nt][2] + b0); v[nt][3] = lp_silu(acc[nt][3] + b1);
             }
             if (POST) {
                 float acc2[NT][4];
@@ -568,8 +568,8 @@ __global__ void __launch_bounds__(MM_THREADS) stem_conv_kernel(const ConvParams 
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const float b0 = __ldg(q.bias + nt * 8 + cpair), b1 = __ldg(q.bias + nt * 8 + cpair + 1);
-                    w[nt][0] = act1(acc2[nt][0] + b0, q.act); w[nt][1] = act1(acc2[nt][1] + b1, q.act);
-                    w[nt][2] = act1(acc2[nt][2] + b0, q.act); w[nt][3] = act1(acc2[nt][3] + b1, q.act);
+                    w[nt][0] = lp_silu(acc2[nt][0] + b0); w[nt][1] = lp_silu(acc2[nt][1] + b1);
+                    w[nt][2] = lp_silu(acc2[nt][2] + b0); w[nt][3] = lp_silu(acc2[nt][3] + b1);
                 }
             } else {
 #pragma unroll
@@ -654,6 +654,7 @@ int lp_stem_mma_try(lp_ctx* ctx, const ConvParams& p, cudaStream_t st) {
 // ps = the stem, p = the conv that reads ONLY the stem's output, post = its fused 1x1 or nullptr.  0: shapes not covered.
 int lp_stem_conv_try(lp_ctx* ctx, const ConvParams& ps, const ConvParams& p, const ConvParams* post, cudaStream_t st) {
     if (ps.in.fmt != LP_FMT_U8 || ps.ksize != 3 || ps.stride != 2 || ps.cin != 3 || ps.cout != 8) return 0;
+    if (ps.act != LP_ACT_SILU || p.act != LP_ACT_SILU || (post && post->act != LP_ACT_SILU)) return 0;       // the activation is compiled in
     if (ps.in_scale_mean != 0.f || ps.in_scale_std != 1.f || ps.res.base || ps.seg_len != 0 || ps.out_cstride != 1) return 0;
     if ((ps.W * 3) % 16 || (ps.in.img % 16) || ((uintptr_t)ps.in.base % 16) || ps.W % 4 || ps.H % 4) return 0;
     if (p.ksize != 3 || p.stride != 2 || p.cin != 8 || p.cout != 16 || p.H != ps.Ho || p.W != ps.Wo || p.res.base || p.res_first ||
