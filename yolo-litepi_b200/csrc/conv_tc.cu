@@ -1049,11 +1049,17 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     // swizzled A tiles: 1x1 layers whose K splits into 64-channel blocks (same bytes per patch stage as the chunk layout)
     p.a_sw128 = (ctx->tc_sw128 && p.use_tma && op.ksize == 1 && op.cin % 64 == 0 && p.kb_ch == 64) ? 1 : 0;
     // Two issuing warps (split_mma) need a third accumulator piece per stage.  Measured (profiles/r2_notes.md): with
-    // cout <= 32 (four accumulator stages of 3 * cout columns still fit the 512 TMEM columns) the 3x3 layers gain 8-10 %;
-    // at cout = 64 only two stages fit and the MMA warps wait for the epilogue (conv_48: 110 -> 122 us), so those layers
-    // keep one issuing warp and 2 * cout columns.  LP_TC_SPLIT=0 disables, =2 forces it wherever two stages fit.
+    // cout <= 32 (four accumulator stages of 3 * cout columns still fit the 512 TMEM columns) the 3x3 layers gain 8-10 %.
+    // At cout = 64 only two stages fit: with cp.async loaders that lost (conv_48: 110 -> 122 us); with TMA loads (five warps
+    // fewer on the issue ports) it wins on the LONG layers (conv_48 118 -> 108 us, 1x1 96 -> 64 at 40x40 27 -> 23) and still loses where
+    // a CTA sees only a few tiles (20x20 64 -> 64: 24 -> 27), so those need >= 5 tiles per CTA.  LP_TC_SPLIT=0 disables, =2 forces it
+    // wherever two stages fit.
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_SPLIT"); f = e ? atoi(e) : 1; }
-      p.split_mma = (!p.a_sw128 && (f == 2 ? 3 * nb <= 256 : (f == 1 && nb <= 32))) ? 1 : 0; }
+      const long long out_px = (long long)batch * p.Ho * p.Wo;
+      const long long tiles = op.ksize == 1 ? (out_px + TILE_M - 1) / TILE_M
+                                            : (long long)batch * ((p.Wo + TCT_W - 1) / TCT_W) * ((p.Ho + TCT_H - 1) / TCT_H);
+      const bool long_layer = p.use_tma && tiles >= 5ll * ctx->sm_count;
+      p.split_mma = (!p.a_sw128 && (f == 2 ? 3 * nb <= 256 : (f == 1 && (nb <= 32 || (3 * nb <= 256 && long_layer))))) ? 1 : 0; }
     const int acc_cols = (p.split_mma ? 3 : 2) * nb;
     p.acc_stride = (acc_cols + 31) / 32 * 32;        // [Ahi*Bhi(+Alo*Bhi) | Ahi*Blo | Alo*Bhi]
     p.acc_stages = 512 / p.acc_stride > MAX_AST ? MAX_AST : 512 / p.acc_stride;
