@@ -1055,9 +1055,11 @@ static int conv_tc_block(lp_ctx* ctx, lp_net_plan& net, const lp_op_desc& op, in
     // a CTA sees only a few tiles (20x20 64 -> 64: 24 -> 27), so those need >= 5 tiles per CTA.  LP_TC_SPLIT=0 disables, =2 forces it
     // wherever two stages fit.
     { static int f = -1; if (f < 0) { const char* e = getenv("LP_TC_SPLIT"); f = e ? atoi(e) : 1; }
-      const long long out_px = (long long)batch * p.Ho * p.Wo;
+      // from the plan's CAPACITY (max_batch), never from the batch of this call: one and two issuers sum the three products in a
+      // different order, and a frame's result must not depend on how many frames travel with it (test_full_batch_properties)
+      const long long out_px = (long long)net.max_batch * p.Ho * p.Wo;
       const long long tiles = op.ksize == 1 ? (out_px + TILE_M - 1) / TILE_M
-                                            : (long long)batch * ((p.Wo + TCT_W - 1) / TCT_W) * ((p.Ho + TCT_H - 1) / TCT_H);
+                                            : (long long)net.max_batch * ((p.Wo + TCT_W - 1) / TCT_W) * ((p.Ho + TCT_H - 1) / TCT_H);
       const bool long_layer = p.use_tma && tiles >= 5ll * ctx->sm_count;
       p.split_mma = (!p.a_sw128 && (f == 2 ? 3 * nb <= 256 : (f == 1 && (nb <= 32 || (3 * nb <= 256 && long_layer))))) ? 1 : 0; }
     const int acc_cols = (p.split_mma ? 3 : 2) * nb;
