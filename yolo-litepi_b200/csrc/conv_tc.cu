@@ -26,12 +26,15 @@
 // thread; one CTA per SM, static round-robin over tiles):
 //   warps 0-3   store warps: staging tile -> global, coalesced               <- stage_full / -> stage_empty
 //               (two staging buffers; layers with room for only one copy it out with the epilogue warps)
-//   warps 4-8   patch loaders (cp.async 16 B, zero-fill halo)                <- patch_empty / -> patch_full
+//   warps 4-8   patch loaders.  Default: ONE thread issues TMA tensor copies (cp.async.bulk.tensor tile mode, zero fill by the copy
+//               engine; 16-byte chunk rows, or whole 128-byte pixel rows into SWIZZLE_128B tiles on the 1x1 layers with cin % 64 == 0;
+//               element strides 2 x 2 pick one parity phase per copy on the stride-2 layers) and patch_full counts bytes; the other
+//               loader threads idle.  LP_TC_TMA=0: all five warps issue cp.async 16 B with zero-fill  <- patch_empty / -> patch_full
 //   warp  9     weight producer (one lane, bulk TMA)                         <- w_empty   / -> w_full
 //   warps 10-17 epilogue: TMEM -> bias/act/residual/split -> staging tile    <- acc_full, stage_empty / -> acc_empty, stage_full
 //               (TMEM quadrant = warp % 4, column half = (warp - 10) / 4)
 //   warp  19    TMEM allocator + MMA issuer A (one lane): Ahi x [Bhi|Blo]     <- patch_full, w_full, acc_empty
-//   warp  18    MMA issuer B: Alo x Bhi into its own accumulator columns (split_mma; see below)
+//   warp  18    MMA issuer B: Alo x Bhi into its own accumulator columns (split_mma: cout <= 32, and cout <= 85 on long layers)
 //   (ids ascend with how critical the role's instruction stream is: the sub-partition arbiter prefers the highest id)
 // Up to 8 patch stages and 4 TMEM accumulator stages keep several tiles in flight: the small-channel
 // layers are HBM/latency-bound, so tiles i+1.. load and tile i-1 drains while tile i is in the tensor core.
