@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(256) detect_tail_kernel(const float* __restric
     float s = 0.f, d = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const float e = expf(x[i] - m);
+        float e;                                  // ex2.approx of a non-positive argument: relative error 2^-22, 1e-4 px on the box after
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x[i] - m) * 1.4426950408889634f));   // the x stride / ratio scaling (expf: 5x the instructions)
         s += e;
         d += e * (float)i;
     }
